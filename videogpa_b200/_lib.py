@@ -1,0 +1,84 @@
+"""ctypes binding of libvideogpa_b200.so (the C-ABI declared in include/videogpa_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is
+raised (the reference CLIs catch ``Exception`` per item and continue, generate/CogVideoX-5B.py:79).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvideogpa_b200.so"
+_lib = None
+
+c_void_p = C.c_void_p
+c_int = C.c_int
+c_i32 = C.c_int32
+c_i64 = C.c_int64
+c_float = C.c_float
+c_double = C.c_double
+c_fp = C.POINTER(C.c_float)
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ("A", c_void_p), ("W", c_void_p), ("bias", c_void_p), ("out", c_void_p),
+        ("M", c_i32), ("N", c_i32), ("K", c_i32), ("lda", c_i32), ("ldo", c_i32),
+        ("epilogue", c_i32), ("rows_per_sample", c_i32), ("text_rows", c_i32),
+        ("gate_txt", c_void_p), ("gate_vid", c_void_p), ("gate_stride_b", c_i64),
+        ("ln_q_w", c_void_p), ("ln_q_b", c_void_p), ("ln_k_w", c_void_p), ("ln_k_b", c_void_p),
+        ("ln_eps", c_float),
+        ("rope_cos", c_void_p), ("rope_sin", c_void_p),
+        ("model_dim", c_i32),
+    ]
+
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV = 0, 1, 2, 3
+
+# name -> (restype, argtypes); every symbol include/videogpa_b200.h declares must be listed here
+# (tests/test_abi.py cross-checks this table against the header).
+SIGNATURES = {
+    "vgpa_last_error": (C.c_char_p, []),
+    "vgpa_abi_version": (c_int, []),
+    "vgpa_device_sm_count": (c_int, []),
+    "vgpa_linear_bf16": (c_int, [C.POINTER(LinearArgs), c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -m videogpa_b200.build` "
+            "(there is no CPU or PyTorch fallback for the CUDA hot path)")
+    lib = C.CDLL(os.fspath(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().vgpa_last_error()
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg.decode(errors='replace') if msg else ''}")
+
+
+def ptr(t) -> int | None:
+    """Device/host address of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
