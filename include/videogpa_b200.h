@@ -44,8 +44,10 @@ enum {
   VGPA_EPI_BIAS = 0,      /* out = acc + bias                                                      */
   VGPA_EPI_BIAS_GELU = 1, /* out = gelu_tanh(acc + bias)              (FeedForward net.0)          */
   VGPA_EPI_GATE_RES = 2,  /* out = out + gate[b, seg(row)] * (acc + bias)   (adaLN-zero residual)  */
-  VGPA_EPI_QKV = 3        /* fused to_q|to_k|to_v: per-head LayerNorm(64) on q,k + 3-D RoPE on     */
+  VGPA_EPI_QKV = 3,       /* fused to_q|to_k|to_v: per-head LayerNorm(64) on q,k + 3-D RoPE on     */
                           /* video rows; v passes through      (CogVideoXAttnProcessor2_0)         */
+  VGPA_EPI_ACCUM = 4      /* out = bf16(out + alpha * acc), one rounding (PEFT LoRA merge,         */
+                          /* generate/CogVideoX-5B.py:29-30: W <- W + (lora_alpha/r) * B @ A)      */
 };
 
 typedef struct vgpa_linear_args {
@@ -71,9 +73,93 @@ typedef struct vgpa_linear_args {
   const float* rope_cos; /* [video rows, 64] fp32, repeat-interleaved pairs, or NULL (training    */
   const float* rope_sin; /*   step passes no image_rotary_emb, 03_train.py:134-139)               */
   int32_t model_dim;     /* D: q cols [0,D), k cols [D,2D), v cols [2D,3D); head_dim is 64        */
+  float alpha;           /* VGPA_EPI_ACCUM scale                                                  */
 } vgpa_linear_args;
 
 int vgpa_linear_bf16(const vgpa_linear_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 — joint text+video full attention: out = softmax(q k^T * scale) v per (batch, head), bf16 in/out,
+ * fp32 softmax, head_dim 64. Replaces F.scaled_dot_product_attention inside diffusers'
+ * CogVideoXAttnProcessor2_0.__call__ (reference call sites
+ * generate/CogVideoX-5B.py:72-77, train/CogVideoX-5B/03_train.py:134-151). No mask, no dropout,
+ * not causal. Heads are packed along the row: head h of row s lives at columns [h*64, h*64+64).
+ * q/k/v may alias one fused [B*S, 3*H*64] projection buffer (pass three pointers into it).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vgpa_attention_args {
+  const void* q;   /* [B, Sq,  >=H*64] bf16 */
+  const void* k;   /* [B, Skv, >=H*64] bf16 */
+  const void* v;   /* [B, Skv, >=H*64] bf16 */
+  void* out;       /* [B, Sq,  >=H*64] bf16 */
+  int32_t B, H, Sq, Skv, head_dim;
+  float scale;     /* softmax scale; <= 0 means 1/sqrt(head_dim) */
+  int64_t q_row_stride, k_row_stride, v_row_stride, out_row_stride;         /* elements */
+  int64_t q_batch_stride, k_batch_stride, v_batch_stride, out_batch_stride; /* elements */
+} vgpa_attention_args;
+
+int vgpa_attention_bf16(const vgpa_attention_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3 — fused LayerNorm + adaLN modulation: out = LN(x) * (1 + scale[b, seg]) + shift[b, seg].
+ * Replaces CogVideoXLayerNormZero / AdaLayerNorm / norm_final of CogVideoXTransformer3DModel
+ * (SURVEY.md App. A.1). seg = text for the first text_rows rows of each sample, video otherwise.
+ * All modulation pointers NULL = plain LayerNorm. ln_weight/ln_bias NULL = no elementwise affine.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vgpa_layernorm_args {
+  const void* x;  /* [rows, ldx] bf16 */
+  void* out;      /* [rows, ldo] bf16 */
+  int32_t rows, D;
+  int64_t ldx, ldo;
+  const void* ln_weight; /* [D] bf16 or NULL */
+  const void* ln_bias;   /* [D] bf16 or NULL */
+  float eps;
+  int32_t rows_per_sample, text_rows;
+  const void* shift_txt; /* [B][D] bf16, batch stride mod_stride_b elements */
+  const void* scale_txt;
+  const void* shift_vid;
+  const void* scale_vid;
+  int64_t mod_stride_b;
+} vgpa_layernorm_args;
+
+int vgpa_layernorm_modulate_bf16(const vgpa_layernorm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conditioning path and patch (un)embedding helpers.
+ * ---------------------------------------------------------------------------------------------- */
+enum { VGPA_ACT_NONE = 0, VGPA_ACT_SILU = 1 };
+/* out[M, N] = bias + act_in(x[M, K]) . W[N, K]^T, M <= 8 (time_embedding.linear_{1,2}, adaLN linears) */
+int vgpa_linear_smallm_bf16(const void* x, const void* W, const void* bias, void* out, int M, int N, int K,
+                            int64_t ldx, int64_t ldo, int act_in, void* stream);
+/* diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): out[B, dim] bf16 */
+int vgpa_timestep_embedding_bf16(const float* d_timesteps, void* out, int B, int dim, void* stream);
+/* [BF, C, H, W] -> [BF*(H/2)*(W/2), C*4] (feature = c*4 + ph*2 + pw) and its inverse (input row stride ldi) */
+int vgpa_patchify_bf16(const void* in, void* out, int BF, int C, int H, int W, void* stream);
+int vgpa_unpatchify_bf16(const void* in, void* out, int BF, int C, int H, int W, int64_t ldi, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CFG combine + v-prediction scheduler update in one pass (CogVideoXPipeline
+ * denoise loop + CogVideoXDDIMScheduler.step / CogVideoXDPMScheduler.step).
+ *   v        = pred_uncond + guidance * (pred_cond - pred_uncond)      (pred_uncond NULL: v = pred_cond)
+ *   x0       = bf16(sqrt_alpha_t * x) - sqrt_beta_t * v
+ *   DDIM:  prev = bf16(c_sample * x) + c_x0 * x0
+ *   DPM :  prev = bf16(c_sample * x) + c_x0 * x0 + c_x0_old * x0_old + c_noise * noise
+ * x0_out (fp32, optional) receives x0 for the multistep solver.
+ * ---------------------------------------------------------------------------------------------- */
+enum { VGPA_SCHED_DDIM = 0, VGPA_SCHED_DPM = 1 };
+typedef struct vgpa_sched_args {
+  const void* pred_uncond; /* [n] bf16 or NULL */
+  const void* pred_cond;   /* [n] bf16 */
+  const void* sample;      /* [n] bf16 */
+  void* prev_sample;       /* [n] bf16 */
+  const float* x0_old;     /* [n] fp32 or NULL */
+  float* x0_out;           /* [n] fp32 or NULL */
+  const void* noise;       /* [n] bf16 or NULL */
+  int64_t n;
+  int32_t mode;
+  float guidance, sqrt_alpha_t, sqrt_beta_t, c_sample, c_x0, c_x0_old, c_noise;
+} vgpa_sched_args;
+
+int vgpa_cfg_scheduler_step(const vgpa_sched_args* args, void* stream);
 
 #ifdef __cplusplus
 }

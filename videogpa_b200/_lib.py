@@ -31,10 +31,46 @@ class LinearArgs(C.Structure):
         ("ln_eps", c_float),
         ("rope_cos", c_void_p), ("rope_sin", c_void_p),
         ("model_dim", c_i32),
+        ("alpha", c_float),
     ]
 
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV = 0, 1, 2, 3
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("out", c_void_p),
+        ("B", c_i32), ("H", c_i32), ("Sq", c_i32), ("Skv", c_i32), ("head_dim", c_i32),
+        ("scale", c_float),
+        ("q_row_stride", c_i64), ("k_row_stride", c_i64), ("v_row_stride", c_i64), ("out_row_stride", c_i64),
+        ("q_batch_stride", c_i64), ("k_batch_stride", c_i64), ("v_batch_stride", c_i64), ("out_batch_stride", c_i64),
+    ]
+
+
+class LayerNormArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("out", c_void_p),
+        ("rows", c_i32), ("D", c_i32),
+        ("ldx", c_i64), ("ldo", c_i64),
+        ("ln_weight", c_void_p), ("ln_bias", c_void_p),
+        ("eps", c_float),
+        ("rows_per_sample", c_i32), ("text_rows", c_i32),
+        ("shift_txt", c_void_p), ("scale_txt", c_void_p), ("shift_vid", c_void_p), ("scale_vid", c_void_p),
+        ("mod_stride_b", c_i64),
+    ]
+
+
+class SchedArgs(C.Structure):
+    _fields_ = [
+        ("pred_uncond", c_void_p), ("pred_cond", c_void_p), ("sample", c_void_p), ("prev_sample", c_void_p),
+        ("x0_old", c_void_p), ("x0_out", c_void_p), ("noise", c_void_p),
+        ("n", c_i64), ("mode", c_i32),
+        ("guidance", c_float), ("sqrt_alpha_t", c_float), ("sqrt_beta_t", c_float),
+        ("c_sample", c_float), ("c_x0", c_float), ("c_x0_old", c_float), ("c_noise", c_float),
+    ]
+
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV, EPI_ACCUM = 0, 1, 2, 3, 4
+ACT_NONE, ACT_SILU = 0, 1
+SCHED_DDIM, SCHED_DPM = 0, 1
 
 # name -> (restype, argtypes); every symbol include/videogpa_b200.h declares must be listed here
 # (tests/test_abi.py cross-checks this table against the header).
@@ -43,6 +79,13 @@ SIGNATURES = {
     "vgpa_abi_version": (c_int, []),
     "vgpa_device_sm_count": (c_int, []),
     "vgpa_linear_bf16": (c_int, [C.POINTER(LinearArgs), c_void_p]),
+    "vgpa_attention_bf16": (c_int, [C.POINTER(AttentionArgs), c_void_p]),
+    "vgpa_layernorm_modulate_bf16": (c_int, [C.POINTER(LayerNormArgs), c_void_p]),
+    "vgpa_linear_smallm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_i64, c_int, c_void_p]),
+    "vgpa_timestep_embedding_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "vgpa_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vgpa_unpatchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p]),
+    "vgpa_cfg_scheduler_step": (c_int, [C.POINTER(SchedArgs), c_void_p]),
 }
 
 

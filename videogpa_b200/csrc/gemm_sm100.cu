@@ -39,6 +39,7 @@ struct EpiParams {
   const float* rope_cos;
   const float* rope_sin;
   int model_dim;
+  float alpha;
 };
 
 template <int BN>
@@ -101,6 +102,22 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
           const float y0 = bf16_round(v[i * 8 + 2 * j]), y1 = bf16_round(v[i * 8 + 2 * j + 1]);
           v[i * 8 + 2 * j] = rr.x + bf16_round(gf.x * y0);
           v[i * 8 + 2 * j + 1] = rr.y + bf16_round(gf.y * y1);
+        }
+      }
+    }
+  } else if constexpr (EPI == VGPA_EPI_ACCUM) {
+    // out <- bf16(out + alpha * acc): one rounding (PEFT merge `weight += scaling * B @ A`)
+    if (live) {
+      const uint4* rp = reinterpret_cast<const uint4*>(orow);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 r = rp[i];
+        const uint32_t ru[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 rr = unpack_bf16x2(ru[j]);
+          v[i * 8 + 2 * j] = rr.x + ep.alpha * v[i * 8 + 2 * j];
+          v[i * 8 + 2 * j + 1] = rr.y + ep.alpha * v[i * 8 + 2 * j + 1];
         }
       }
     }
@@ -346,6 +363,7 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
   ep.ln_eps = a->ln_eps;
   ep.rope_cos = a->rope_cos; ep.rope_sin = a->rope_sin;
   ep.model_dim = a->model_dim;
+  ep.alpha = a->alpha;
   if (a->epilogue == VGPA_EPI_QKV) {
     VGPA_CHECK(a->model_dim > 0 && a->model_dim % 64 == 0 && a->N == 3 * a->model_dim,
                "vgpa_linear_bf16: QKV epilogue needs N == 3*model_dim (N=%d model_dim=%d)", a->N, a->model_dim);
@@ -379,6 +397,7 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
     VGPA_GEMM_DISPATCH(VGPA_EPI_BIAS_GELU)
     VGPA_GEMM_DISPATCH(VGPA_EPI_GATE_RES)
     VGPA_GEMM_DISPATCH(VGPA_EPI_QKV)
+    VGPA_GEMM_DISPATCH(VGPA_EPI_ACCUM)
     default:
       break;
   }
