@@ -161,6 +161,83 @@ typedef struct vgpa_sched_args {
 
 int vgpa_cfg_scheduler_step(const vgpa_sched_args* args, void* stream);
 
+/* ================================================================================================
+ * Geometry-consistency scorer (SURVEY.md §8 rows a-10 ... a-15). All pointers are DEVICE pointers;
+ * every entry point is asynchronous on `stream`. Workspaces are caller-owned, 256-byte aligned.
+ * ============================================================================================== */
+
+/* K5 — MVCS for a batch of clips: replaces MVCSMetric.compute (metrics/mvcs.py:12-114).
+ *   depths [n_clips, T, H, W] fp32; intrinsics [n_clips, T, k_dim, k_dim] (k_dim 3 or 4, top-left 3x3 used);
+ *   extrinsics [n_clips, T, e_rows, 4] world->camera (e_rows 3 or 4).
+ *   pair_mse / pair_cnt [n_clips, T-1] (optional): masked MSE and mask size of pair (i, i+1);
+ *   scores [n_clips] fp64 = exp(-mean of the non-empty pairs' MSE), 0.0 when no pair contributes. */
+size_t vgpa_mvcs_workspace_bytes(int n_clips, int T, int H, int W);
+int vgpa_mvcs_blocks_per_pair(int n_clips, int T, int H, int W);
+int vgpa_mvcs_batch(const float* d_depths, const float* d_intrinsics, const float* d_extrinsics, int n_clips, int T,
+                    int H, int W, int k_dim, int e_rows, void* d_workspace, size_t workspace_bytes,
+                    double* d_pair_mse, int64_t* d_pair_cnt, double* d_scores, void* stream);
+
+/* K6 — reprojection renderer: replaces batch_reproject / project_points (utils/projection_utils.py:12-101).
+ *   points, colors [N, 3] fp32; intrinsics [T, 3, 3]; extrinsics [T, e_rows, 4]; out [T, 3, H, W] fp32 in [-1, 1].
+ *   Nearest z wins; exact z ties go to the lowest point index. */
+size_t vgpa_reproject_workspace_bytes(int T, int H, int W);
+int vgpa_reproject_batch(const float* d_points, const float* d_colors, const float* d_intrinsics,
+                         const float* d_extrinsics, int64_t n_points, int T, int H, int W, int e_rows,
+                         void* d_workspace, size_t workspace_bytes, float* d_out, void* stream);
+
+/* K7 — coloured point cloud: replaces get_colored_pointcloud (utils/pointcloud_utils.py:10-80).
+ *   points [N, 3], conf [N], images [T, 3, H, W] (images_nhwc = 0) or [T, H, W, 3] (= 1) in [0, 1], N = T*H*W.
+ *   Keeps finite conf > 1e-5 and, for conf_thres > 0, conf >= the k-th largest valid value with
+ *   k = max(1, ceil(N_valid * (1 - conf_thres/100))). Survivors keep their order. out_count receives N'. */
+size_t vgpa_pointcloud_workspace_bytes(int64_t n_points);
+int vgpa_pointcloud_filter(const float* d_points, const float* d_images, const float* d_conf, int64_t n_points,
+                           int hw_per_frame, int images_nhwc, double conf_thres, void* d_workspace,
+                           size_t workspace_bytes, float* d_out_vertices, float* d_out_colors, int64_t* d_out_count,
+                           float* d_out_threshold, void* stream);
+
+/* K8 — fundamental matrix + Sampson distance per frame pair: replaces kornia find_fundamental +
+ * sampson_epipolar_distance as used by metrics/epipolar.py:194-216.
+ *   pts1, pts2 [n_pairs, max_matches, 2] fp32; counts [n_pairs] (NULL = all max_matches);
+ *   F [n_pairs, 3, 3]; mean_dist [n_pairs] = mean sqrt(d^2 + 1e-8); valid [n_pairs] (0 when < 8 matches or NaN). */
+int vgpa_epipolar_batch(const float* d_pts1, const float* d_pts2, const int32_t* d_counts, int n_pairs, int max_matches,
+                        float* d_F, float* d_mean_dist, int32_t* d_valid, void* stream);
+
+/* Consistency-score geometry: compute_motion_score_vectorized (metrics/consistency_score.py:8-38),
+ * MSEMetric.compute with its range heuristics (metrics/mse.py:14-54), and the DA3 depth un-projection
+ * (pipelines/process_video.py:151-156). kind: 0 = fp32, 1 = uint8; nhwc: source layout; numpy: the
+ * reference's ndarray branch (only `max > 1 -> /255`). */
+int vgpa_motion_score(const float* d_extrinsics, int T, int e_rows, float* d_out, void* stream);
+size_t vgpa_mse_workspace_bytes(void);
+int vgpa_mse_range_normalized(const void* d_gt, int gt_kind, int gt_nhwc, int gt_numpy, const void* d_rep, int rep_kind,
+                              int rep_nhwc, int rep_numpy, int64_t N, int C, int H, int W, void* d_workspace,
+                              size_t workspace_bytes, float* d_out, void* stream);
+int vgpa_unproject_depth(const float* d_depth, const float* d_intrinsics, const float* d_extrinsics_w2c, int T, int H,
+                         int W, int e_rows, float* d_out_points, void* stream);
+
+/* K9 — DPO loss: replaces DPOLoss.forward (train/loss.py:53-121) and its autograd.
+ *   tensors[6] = v_win, v_lose, v_win_ref, v_lose_ref, v_win_target, v_lose_target, each [B, n_per_sample],
+ *   fp32 (is_bf16 = 0) or bf16 (= 1). out5 = loss, reward_margin, winner_reward, loser_reward, accuracy.
+ *   err4 [4, B] (optional) = model_win, model_lose, ref_win, ref_lose MSEs. coef [2, B] (needed for
+ *   backward) = dLoss/d(model_win_err), dLoss/d(model_lose_err). */
+enum { VGPA_DPO_SIGMOID = 0, VGPA_DPO_HINGE = 1, VGPA_DPO_SFT = 2 /* loss = mean MSE(tensors[0], tensors[4]) */ };
+typedef struct vgpa_dpo_args {
+  const void* tensors[6];
+  int32_t is_bf16[6];
+  int32_t B;
+  int64_t n_per_sample;
+  float beta, label_smoothing;
+  int32_t loss_type;
+  float* d_out5;
+  float* d_err4;
+  float* d_coef;
+  void* d_workspace;
+  size_t workspace_bytes;
+} vgpa_dpo_args;
+size_t vgpa_dpo_workspace_bytes(int B, int64_t n_per_sample);
+int vgpa_dpo_loss_forward(const vgpa_dpo_args* args, void* stream);
+int vgpa_dpo_loss_backward(const vgpa_dpo_args* args, const float* d_grad_loss, void* d_grad_win, void* d_grad_lose,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """Build (if needed) and load the C-ABI library."""
+    from videogpa_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    gdir = os.path.join(ROOT, "tests", "golden")
+    return lambda name: np.load(os.path.join(gdir, name + ".npz"))

@@ -58,6 +58,16 @@ class LayerNormArgs(C.Structure):
     ]
 
 
+class DpoArgs(C.Structure):
+    _fields_ = [
+        ("tensors", c_void_p * 6), ("is_bf16", c_i32 * 6),
+        ("B", c_i32), ("n_per_sample", c_i64),
+        ("beta", c_float), ("label_smoothing", c_float), ("loss_type", c_i32),
+        ("d_out5", c_void_p), ("d_err4", c_void_p), ("d_coef", c_void_p),
+        ("d_workspace", c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class SchedArgs(C.Structure):
     _fields_ = [
         ("pred_uncond", c_void_p), ("pred_cond", c_void_p), ("sample", c_void_p), ("prev_sample", c_void_p),
@@ -86,6 +96,25 @@ SIGNATURES = {
     "vgpa_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vgpa_unpatchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p]),
     "vgpa_cfg_scheduler_step": (c_int, [C.POINTER(SchedArgs), c_void_p]),
+    "vgpa_mvcs_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int, c_int]),
+    "vgpa_mvcs_blocks_per_pair": (c_int, [c_int, c_int, c_int, c_int]),
+    "vgpa_mvcs_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                C.c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vgpa_reproject_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
+    "vgpa_reproject_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p,
+                                     C.c_size_t, c_void_p, c_void_p]),
+    "vgpa_pointcloud_workspace_bytes": (C.c_size_t, [c_i64]),
+    "vgpa_pointcloud_filter": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_double, c_void_p, C.c_size_t,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vgpa_epipolar_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vgpa_motion_score": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "vgpa_mse_workspace_bytes": (C.c_size_t, []),
+    "vgpa_mse_range_normalized": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_i64, c_int, c_int,
+                                          c_int, c_void_p, C.c_size_t, c_void_p, c_void_p]),
+    "vgpa_unproject_depth": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vgpa_dpo_workspace_bytes": (C.c_size_t, [c_int, c_i64]),
+    "vgpa_dpo_loss_forward": (c_int, [C.POINTER(DpoArgs), c_void_p]),
+    "vgpa_dpo_loss_backward": (c_int, [C.POINTER(DpoArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

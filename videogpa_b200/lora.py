@@ -1,0 +1,92 @@
+"""PEFT LoRA adapter loading and merge for the `--lora_path` surface.
+
+Reference: generate/CogVideoX-5B.py:24-31 (`PeftModel.from_pretrained(...).merge_and_unload()`),
+scaling overrides in generate/CogVideoX1.5-5B.py:32-35 (absolute) and generate/Wan2.2-TI2V-5B.py:66-70
+(multiplicative), adapter format checkpoints/*/adapter_config.json + adapter_model.safetensors
+(download_ckpt.py:40-61). Merge rule: W <- W + (lora_alpha / r) * B @ A for attn1.{to_q,to_k,to_v,to_out.0}
+(fp32 product, one rounding to bf16).
+
+The product runs on the tcgen05 GEMM: the fp32 adapter matrices are split into bf16 hi + lo parts and
+concatenated along K so that one GEMM (K = 3r) accumulates B_hi A_hi + B_hi A_lo + B_lo A_hi in fp32
+(relative error ~2^-16 of the delta), and the VGPA_EPI_ACCUM epilogue adds it to W with one rounding.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+
+import torch
+
+from . import dense
+
+_KEY = re.compile(r"(?:base_model\.model\.)?transformer_blocks\.(\d+)\.attn1\.(to_q|to_k|to_v|to_out\.0)\.lora_(A|B)(?:\.default)?\.weight$")
+
+
+def read_adapter(lora_path: str):
+    """-> (config dict, {(layer, module): (A [r, in], B [out, r])}) from a PEFT adapter directory."""
+    cfg_file = os.path.join(lora_path, "adapter_config.json")
+    if not os.path.isfile(cfg_file):
+        raise RuntimeError(f"{cfg_file} not found: not a PEFT adapter directory")
+    with open(cfg_file, "r", encoding="utf-8") as f:
+        cfg = json.load(f)
+    if cfg.get("peft_type", "LORA") != "LORA" or cfg.get("use_dora") or cfg.get("use_rslora") or cfg.get("fan_in_fan_out"):
+        raise RuntimeError("only plain LoRA adapters (no DoRA / rsLoRA / fan_in_fan_out) are supported")
+    st_file = os.path.join(lora_path, "adapter_model.safetensors")
+    if os.path.isfile(st_file):
+        from safetensors.torch import load_file
+        tensors = load_file(st_file)
+    elif os.path.isfile(os.path.join(lora_path, "adapter_model.bin")):
+        tensors = torch.load(os.path.join(lora_path, "adapter_model.bin"), map_location="cpu")
+    else:
+        raise RuntimeError(f"no adapter_model.safetensors under {lora_path}")
+    pairs: dict = {}
+    for k, v in tensors.items():
+        m = _KEY.search(k)
+        if not m:
+            continue
+        key = (int(m.group(1)), m.group(2))
+        pairs.setdefault(key, {})[m.group(3)] = v
+    out = {}
+    for key, ab in pairs.items():
+        if "A" not in ab or "B" not in ab:
+            raise RuntimeError(f"adapter is missing lora_A or lora_B for {key}")
+        out[key] = (ab["A"], ab["B"])
+    if not out:
+        raise RuntimeError("no attn1 LoRA tensors found in the adapter")
+    return cfg, out
+
+
+def _split_bf16(t: torch.Tensor):
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def merge_lora(transformer, lora_path: str, scaling: float | None = None, weight: float | None = None) -> int:
+    """Merge the adapter into `transformer` in place. scaling = absolute override; weight multiplies alpha/r.
+
+    Returns the number of merged modules.
+    """
+    cfg, pairs = read_adapter(lora_path)
+    base = float(cfg["lora_alpha"]) / float(cfg["r"])
+    s = base if scaling is None else float(scaling)
+    if weight is not None:
+        s = s * float(weight)
+    dev = transformer.device
+    n = 0
+    for (layer, module), (A, B) in sorted(pairs.items()):
+        if layer >= len(transformer.blocks):
+            raise RuntimeError(f"adapter targets layer {layer}, the model has {len(transformer.blocks)}")
+        W = transformer.attention_weight(layer, module)                      # [out, in] bf16 view, updated in place
+        A = A.to(device=dev, dtype=torch.float32)                            # [r, in]
+        B = B.to(device=dev, dtype=torch.float32)                            # [out, r]
+        if B.shape[0] != W.shape[0] or A.shape[1] != W.shape[1] or A.shape[0] != B.shape[1]:
+            raise RuntimeError(f"LoRA shape mismatch at layer {layer} {module}: A {tuple(A.shape)} B {tuple(B.shape)} W {tuple(W.shape)}")
+        Bh, Bl = _split_bf16(B)
+        Ah, Al = _split_bf16(A.t().contiguous())                             # [in, r]
+        a_op = torch.cat([Bh, Bh, Bl], dim=1).contiguous()                   # [out, 3r]
+        w_op = torch.cat([Ah, Al, Ah], dim=1).contiguous()                   # [in, 3r]  (N = in features)
+        dense.linear(a_op, w_op, None, out=W, epilogue=dense.EPI_ACCUM, alpha=s)
+        n += 1
+    return n

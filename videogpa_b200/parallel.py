@@ -1,0 +1,99 @@
+"""One-process-per-GPU sharding of the denoise-and-score path.
+
+The reference shards independent work items over processes with no collective
+(`items[i::num_gpus]`, replicate.py:119-133; contiguous chunks for scoring, replicate_scorer.py:244-250).
+Here the processes are torch.distributed ranks (NCCL over NVLink on the GPU box, gloo in the CPU
+tests) and the only exchanges are
+  * CfgPairGroup.exchange — 2-rank all-gather of the noise prediction, once per denoise step, when the
+    cond/uncond pair of one prompt is split over two GPUs (4.5 MB fp32-equivalent for CogVideoX);
+  * gather_frames / gather_scores — the final gather of decoded uint8 frames or of scalar scores to rank 0.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun). Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_round_robin(items, rank: int, world: int):
+    """Prompt shard: rank r takes items r, r+world, ... (replicate.py:120)."""
+    return list(items)[rank::world]
+
+
+def shard_contiguous(items, rank: int, world: int):
+    """Scorer shard: contiguous chunks, remainder spread over the first ranks (replicate_scorer.py:244-250)."""
+    items = list(items)
+    base, rem = divmod(len(items), world)
+    start = rank * base + min(rank, rem)
+    return items[start:start + base + (1 if rank < rem else 0)]
+
+
+class CfgPairGroup:
+    """Ranks (2p, 2p+1) hold the uncond / cond branch of prompt-group p."""
+
+    def __init__(self, rank: int, world: int):
+        if world % 2 != 0:
+            raise RuntimeError("CFG-pair sharding needs an even number of ranks")
+        self.rank, self.world = rank, world
+        self.pair = rank // 2
+        self.branch = rank % 2            # 0 = uncond (negative prompt), 1 = cond
+        self.group = None
+        for p in range(world // 2):       # every rank must take part in every new_group call
+            g = dist.new_group(ranks=[2 * p, 2 * p + 1])
+            if p == self.pair:
+                self.group = g
+
+    def exchange(self, pred: torch.Tensor):
+        """-> (pred_uncond, pred_cond), identical on both ranks of the pair."""
+        pred = pred.contiguous()
+        both = torch.empty((2,) + tuple(pred.shape), dtype=pred.dtype, device=pred.device)
+        dist.all_gather_into_tensor(both.view(-1), pred.view(-1), group=self.group)
+        return both[0], both[1]
+
+
+def gather_frames(frames: torch.Tensor, rank: int, world: int, dst: int = 0):
+    """Final decoded-frame gather: every rank contributes a [n_i, ...] uint8 tensor with identical trailing
+    shape; rank `dst` receives the list ordered by rank, the others get None."""
+    if world == 1:
+        return [frames]
+    n = torch.tensor([frames.shape[0]], dtype=torch.int64, device=frames.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    nmax = int(max(int(c.item()) for c in counts))
+    pad = torch.zeros((nmax,) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
+    pad[:frames.shape[0]] = frames
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return [b[:int(c.item())] for b, c in zip(bufs, counts)]
+
+
+def gather_scores(scores: torch.Tensor, rank: int, world: int):
+    """All-gather of per-rank score vectors (variable length) -> concatenated tensor in rank order on every rank."""
+    if world == 1:
+        return scores
+    n = torch.tensor([scores.numel()], dtype=torch.int64, device=scores.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    nmax = int(max(int(c.item()) for c in counts))
+    pad = torch.zeros(nmax, dtype=scores.dtype, device=scores.device)
+    pad[:scores.numel()] = scores.reshape(-1)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[:int(c.item())] for b, c in zip(bufs, counts)])
