@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — denoised latent tokens/s of the CogVideoX-5B denoise step on B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one denoise step of one prompt at 49 frames 720x480: the CFG pair (2 DiT forwards, S = 226 text
++ 17 550 video tokens, 42 blocks, D = 3072, 48 heads x 64) + fused guidance/DDIM update. 17 550 latent
+tokens are denoised per step. Weights are random-init at the true 5B shapes, inputs synthetic
+ — no checkpoint or dataset is reachable. With N > 1 every rank denoises its own prompt
+(prompt-batch shard, no data-path collective): weak scaling, value = N * 17 550 * K / max-over-ranks time.
+
+Printed JSON (rank 0): value = device-resident throughput (CUDA events); e2e = the same metric through the
+host-facing pipeline call with pinned host buffers (H2D of latents + prompt embeddings and D2H of the new
+latents inside the timed region); roofline = the attention kernel's FLOP/s against the measured cuBLAS
+bf16 peak; cpu_baseline = the CPU oracle on a bounded sample (one transformer block), extrapolated.
+--impl reference times that CPU restatement of the reference's diffusers path on the host cores (diffusers
+itself is not installable offline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_TEXT, LAT_F, LAT_C, LAT_H, LAT_W = 226, 13, 16, 60, 90
+S_VIDEO = LAT_F * (LAT_H // 2) * (LAT_W // 2)        # 17 550
+METRIC = "denoised latent tokens/sec CogVideoX-5B 49f 720x480"
+UNIT = "tokens/s"
+WORKLOAD = ("CogVideoX-5B T2V, 49 frames 720x480, DDIM denoise step = CFG pair (2 DiT forwards) + guidance + update; "
+            "one prompt per GPU (prompt-batch shard)")
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            try:
+                sm.append(float(parts[0])); mx = max(mx, float(parts[1]))
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_block_sample(threads: int, repeats: int = 1):
+    """Time the CPU oracle (torch restatement of the diffusers math) on ONE transformer block at the full
+    sequence, B = 1, bf16, and extrapolate to a denoise step (42 blocks x 2 CFG branches). Returns
+    (tokens_per_s, seconds_per_block, description)."""
+    import torch
+    from oracle import dit_torch as O
+    torch.set_num_threads(threads)
+    cfg = O.DiTConfig(num_layers=1)
+    sd = O.random_state_dict(cfg, seed=1234, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(42)
+    D = cfg.inner_dim
+    hs = torch.randn(1, S_VIDEO, D, generator=g).to(torch.bfloat16)
+    enc = torch.randn(1, S_TEXT, D, generator=g).to(torch.bfloat16)
+    emb = torch.randn(1, cfg.time_embed_dim, generator=g).to(torch.bfloat16)
+    rope = O.rope_3d(cfg, LAT_F, LAT_H, LAT_W)
+    best = float("inf")
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.block_forward(sd, cfg, 0, hs, enc, emb, rope)
+            best = min(best, time.perf_counter() - t0)
+    step_s = best * 42 * 2
+    return S_VIDEO / step_s, best, "1 of 42 CogVideoXBlocks at S=17776, B=1, bf16, torch CPU; x42 blocks x2 CFG branches extrapolated"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    for _ in range(max(0, args.warmup if args.warmup < 2 else 1)):
+        cpu_block_sample(threads)
+    t_all0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, sec_block, desc = cpu_block_sample(threads)
+        vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * S_VIDEO / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "layers": 42, "tokens_per_step_per_gpu": S_VIDEO, "sequence": S_TEXT + S_VIDEO,
+                       "note": "CPU arm: oracle/dit_torch.py restatement of the reference's diffusers path on the host cores "
+                               "(diffusers/peft are not installable offline, DESIGN.md); each step = a bounded sample, see cpu_baseline.sample"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from videogpa_b200 import _lib, dense
+    from videogpa_b200.metrics import mvcs_batch
+    from videogpa_b200.pipeline import CogVideoXDenoisePipeline
+    from videogpa_b200.schedulers import CogVideoXDDIMScheduler
+    from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = TransformerConfig.cogvideox_5b()
+    if args.layers:
+        cfg.num_layers = args.layers
+    model = CogVideoXTransformer3D.random_init(cfg, seed=1234, device=dev)
+    sched = CogVideoXDDIMScheduler()
+    pipe = CogVideoXDenoisePipeline(model, sched)
+    timesteps = sched.set_timesteps(50)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    latents = pipe.prepare_latents(1, 49, 480, 720, generator=g)
+    pe = torch.randn(2, S_TEXT, cfg.text_embed_dim, generator=torch.Generator(device=dev).manual_seed(43), device=dev).to(torch.bfloat16)
+    rope = pipe.rotary(LAT_F, LAT_H, LAT_W)
+    guidance = 6.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # attention launch timing hook (roofline): events bracket every attention launch of the timed steps
+    attn_events = []
+    orig_attention = dense.attention
+
+    def timed_attention(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_attention(*a, **k)
+        e1.record()
+        attn_events.append((e0, e1))
+        return r
+
+    import videogpa_b200.transformer as tr_mod
+
+    # ---- device-resident throughput
+    lat = latents
+    with torch.no_grad():
+        for i in range(args.warmup):
+            lat = pipe.denoise_step(lat, pe, int(timesteps[i % 50]), guidance, rope)
+        tr_mod.dense.attention = timed_attention
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            lat = pipe.denoise_step(lat, pe, int(timesteps[(args.warmup + i) % 50]), guidance, rope)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        tr_mod.dense.attention = orig_attention
+    ms = e0.elapsed_time(e1)
+    attn_ms = [a.elapsed_time(b) for a, b in attn_events]
+    finite = bool(torch.isfinite(lat.float()).all().item())
+
+    # ---- end to end through the host-facing call (pinned host buffers, H2D + D2H inside the timed region)
+    lat_h = torch.empty(latents.shape, dtype=torch.bfloat16, pin_memory=True); lat_h.copy_(latents)
+    pe_h = torch.empty(pe.shape, dtype=torch.bfloat16, pin_memory=True); pe_h.copy_(pe)
+    out_h = torch.empty(latents.shape, dtype=torch.bfloat16, pin_memory=True)
+    with torch.no_grad():
+        for i in range(min(args.warmup, 2)):
+            pipe.denoise_step_host(lat_h, pe_h, int(timesteps[i]), guidance, rope, out_host=out_h)
+        barrier()
+        t0 = time.perf_counter()
+        cur, nxt = lat_h, out_h
+        for i in range(args.steps):
+            pipe.denoise_step_host(cur, pe_h, int(timesteps[(args.warmup + i) % 50]), guidance, rope, out_host=nxt)
+            torch.cuda.current_stream().synchronize()      # the caller reads the returned host latents every step
+            cur, nxt = nxt, cur
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    h2d = lat_h.numel() * 2 + pe_h.numel() * 2
+    d2h = lat_h.numel() * 2
+
+    # ---- max over ranks
+    times = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    if rank != 0:
+        return
+    tokens = world * S_VIDEO * args.steps
+    value = tokens / (ms_max / 1000.0)
+    e2e_value = tokens / (e2e_ms_max / 1000.0)
+    L = cfg.num_layers
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    attn_flops = 4.0 * 2 * cfg.num_attention_heads * (S_TEXT + S_VIDEO) ** 2 * 64
+    attn_avg_ms = sum(attn_ms) / max(1, len(attn_ms))
+    attn_tf = attn_flops / (attn_avg_ms / 1000.0) / 1e12
+    step_flops = 2 * model.flops_per_sample(S_TEXT, S_VIDEO)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "attention_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- secondary metric of BASELINE.json: MVCS scores/s at the DA3 production size, batched
+    mvcs = None
+    try:
+        N, T, H, W = 128, 10, 504, 504
+        gd = torch.Generator(device=dev).manual_seed(0)
+        depth = 2.0 + 0.5 * torch.rand(N, T, H, W, generator=gd, device=dev)
+        K = torch.tensor([[0.8 * W, 0, W / 2], [0, 0.8 * W, H / 2], [0, 0, 1]], device=dev).expand(N, T, 3, 3).contiguous()
+        E = torch.zeros(N, T, 3, 4, device=dev)
+        import math
+        for i in range(T):
+            a = math.radians(0.5 * i)
+            E[:, i] = torch.tensor([[math.cos(a), 0, math.sin(a), 0.02 * i], [0, 1, 0, 0], [-math.sin(a), 0, math.cos(a), 0]], device=dev)
+        for _ in range(3):
+            mvcs_batch(depth, K, E)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            sc = mvcs_batch(depth, K, E)
+        a1.record(); torch.cuda.synchronize()
+        mms = a0.elapsed_time(a1) / 5
+        mvcs = {"metric": "MVCS scores/sec", "value": N / (mms / 1000.0), "unit": "scores/s", "clips_per_launch": N,
+                "workload": "10 frames 504x504 (DA3 production size), synthetic depth/pose", "ms_per_launch": mms,
+                "hbm_gbs_algorithmic": N * (T - 1) * H * W * 8 / (mms / 1000.0) / 1e9, "hbm_peak_gbs": peak_hbm,
+                "score0": float(sc[0].item())}
+        del depth
+    except Exception as ex:     # the secondary metric never hides the primary line
+        mvcs = {"error": str(ex)}
+
+    # ---- CPU baseline (bounded sample, rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec_block, desc = cpu_block_sample(os.cpu_count() or 1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc, "seconds_per_block": sec_block}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "layers": L, "tokens_per_step_per_gpu": S_VIDEO, "sequence": S_TEXT + S_VIDEO, "guidance_scale": guidance,
+                   "weights": "random-init N(0,0.02^2) at the 5B shapes, seed 1234", "l2": "inputs larger than L2 (11 GB weights + 2 GB activations per step)",
+                   "parallelism": f"dp{world} (prompt shard, no data-path collective)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps},
+        "gpu_launches": args.steps * (model.kernel_launches(2) + 1),
+        "roofline": {"kernel": "attn_fwd_d64_kernel", "bound": "tensor", "achieved": attn_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": attn_tf / peak_tf, "traffic": traffic, "peak_source": peak_src + " bf16_tflops_sustained",
+                     "flops_per_launch": attn_flops, "avg_launch_ms": attn_avg_ms, "launches_timed": len(attn_ms),
+                     "share_of_step": (sum(attn_ms) / ms_max) if ms_max > 0 else None},
+        "step_tflops": step_flops * args.steps / (ms_max / 1000.0) / 1e12,
+        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=0, help="debug: run fewer transformer blocks (the number is printed in config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        from videogpa_b200.parallel import init_from_env
+        init_from_env("nccl")
+    run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

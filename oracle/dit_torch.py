@@ -233,8 +233,8 @@ def trailing_timesteps(num_inference_steps: int, num_train_timesteps: int = 1000
 
 def ddim_step(ac: np.ndarray, t: int, t_prev: int, sample: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     """CogVideoXDDIMScheduler.step, v-prediction, eta = 0 (App. A.4). `sample` keeps its dtype for coef*sample."""
-    a_t = ac[t]
-    a_prev = ac[t_prev] if t_prev >= 0 else 1.0
+    a_t = float(ac[t])
+    a_prev = float(ac[t_prev]) if t_prev >= 0 else 1.0
     x0 = (a_t ** 0.5) * sample - ((1 - a_t) ** 0.5) * v
     a = ((1 - a_prev) / (1 - a_t)) ** 0.5
     b = a_prev ** 0.5 - a_t ** 0.5 * a
@@ -255,8 +255,8 @@ def get_velocity(ac, x, noise, t):
 
 def dpm_coefficients(ac: np.ndarray, t: int, t_prev: int, t_back: int | None):
     """CogVideoXDPMScheduler multipliers (App. A.4): returns (m1, m2, m_noise, r or None)."""
-    a_t = ac[t]
-    a_prev = ac[t_prev] if t_prev >= 0 else 1.0
+    a_t = float(ac[t])
+    a_prev = float(ac[t_prev]) if t_prev >= 0 else 1.0
     lam = lambda a: math.log((a / (1 - a)) ** 0.5)
     lam_t = lam(a_t)
     lam_prev = lam(a_prev) if a_prev < 1.0 else float("inf")

@@ -219,7 +219,9 @@ def test_dpo_loss_golden_and_grad(lib, golden):
         out = DPOLoss(**kw)(*cu)
         assert isinstance(out, LossOutput)
         got = [out.loss.item(), out.reward_margin.item(), out.winner_reward.item(), out.loser_reward.item(), out.accuracy.item()]
-        np.testing.assert_allclose(got, g[tag], rtol=2e-5, atol=2e-6)   # fp32 reference reductions vs fp64 partial sums
+        # fp32 reference reductions vs fp64 partial sums; beta multiplies the ~1e-7 noise of the reference's
+        # fp32 means into the logit, so the loss tolerance scales with beta
+        np.testing.assert_allclose(got, g[tag], rtol=2e-5 * max(1.0, kw["beta"] / 50.0), atol=2e-6)
     x = [torch.from_numpy(a).cuda() for a in g["small_inputs"]]
     x[0].requires_grad_(True); x[1].requires_grad_(True)
     out = create_loss_strategy("dpo", beta=2.0)(*x)
