@@ -257,19 +257,19 @@ def dpm_coefficients(ac: np.ndarray, t: int, t_prev: int, t_back: int | None):
     """CogVideoXDPMScheduler multipliers (App. A.4): returns (m1, m2, m_noise, r or None)."""
     a_t = float(ac[t])
     a_prev = float(ac[t_prev]) if t_prev >= 0 else 1.0
-    lam = lambda a: math.log((a / (1 - a)) ** 0.5)
+
+    def lam(a):  # log-SNR/2 with torch's log(0) = -inf (zero-terminal SNR: ac[999] == 0) and log(inf) = +inf
+        a = float(a)
+        return -math.inf if a <= 0.0 else (math.inf if a >= 1.0 else math.log((a / (1 - a)) ** 0.5))
+
     lam_t = lam(a_t)
-    lam_prev = lam(a_prev) if a_prev < 1.0 else float("inf")
-    h = lam_prev - lam_t
-    if math.isinf(h):
-        m1, m2, mn = 0.0, -1.0 * (a_prev ** 0.5), 0.0               # final step to alpha_prev = 1: x_prev = x0
-    else:
-        m1 = ((1 - a_prev) / (1 - a_t)) ** 0.5 * math.exp(-h)
-        m2 = math.expm1(-2 * h) * a_prev ** 0.5
-        mn = (1 - a_prev) ** 0.5 * (1 - math.exp(-2 * h)) ** 0.5
+    h = lam(a_prev) - lam_t                                            # +inf on the first (a_t = 0) and last (a_prev = 1) step
+    m1 = ((1 - a_prev) / (1 - a_t)) ** 0.5 * math.exp(-h)
+    m2 = math.expm1(-2 * h) * a_prev ** 0.5
+    mn = (1 - a_prev) ** 0.5 * (1 - math.exp(-2 * h)) ** 0.5
     r = None
     if t_back is not None and not math.isinf(h):
-        r = (lam_t - lam(ac[t_back])) / h
+        r = (lam_t - lam(ac[t_back])) / h                              # +inf when t_back = 999: 1/(2r) = 0
     return m1, m2, mn, r
 
 

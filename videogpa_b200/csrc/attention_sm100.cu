@@ -17,9 +17,20 @@
 // operand of the PV MMA. The row max used for the exponentials is allowed to go stale by up to
 // 2^8 (O/l are rescaled only when a row max grows by more than that), which keeps the TMEM
 // read-modify-write of O off the steady-state path; the final O/l is exact.
+//
+// With head_dim 64 there are only 128 MMA FLOPs per softmax element, so the softmax warpgroups (MUFU
+// ex2 at 16/clk/SM, FMA/ALU issue) are the bound, not the tensor pipe. The kernel is therefore built
+// to keep them busy:
+//   * a softmax thread pulls its whole S row (128 fp32) into registers and releases the TMEM S tile
+//     at once (s_free), so S_t(j+1) = Q_t K_{j+1}^T is computed while softmax(j) is still running;
+//   * scale/subtract, row-sum and (part of) the exponentials run as packed f32x2 FMA-pipe ops; NPOLY of
+//     the 64 column pairs of a row use a Cody-Waite + degree-3 polynomial exp2 on the FMA pipe instead
+//     of MUFU (relative error ~1e-4, below the bf16 rounding of P), balancing the two pipes;
+//   * the row max uses 3-input FMNMX3.
 #include "sm100.cuh"
 #include "../../include/videogpa_b200.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace vgpa {
 namespace {
@@ -30,8 +41,7 @@ constexpr int AT_BN = 128;        // kv rows per tile
 constexpr int AT_D = 64;          // head dim
 constexpr int AT_KV_SLOTS = 6;    // ring of 16 KB tiles: K0 V0 K1 V1 ...
 constexpr uint32_t AT_TILE_BYTES = AT_BN * AT_D * 2;        // 16384
-constexpr uint32_t AT_P_BYTES = AT_BM * AT_BN * 2;          // 32768
-constexpr uint32_t AT_SMEM_BYTES = 2 * AT_TILE_BYTES + AT_KV_SLOTS * AT_TILE_BYTES + 2 * AT_P_BYTES + 1024 + 256;
+constexpr uint32_t AT_SMEM_BYTES = 2 * AT_TILE_BYTES + AT_KV_SLOTS * AT_TILE_BYTES + 1024 + 256;
 constexpr uint32_t AT_TMEM_COLS = 512;
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -41,8 +51,118 @@ struct AttnParams {
   long long out_batch_stride;
   int Sq, Skv;
   float scale_log2;
+  int stagger_cycles;
+  int issuer_mode;
 };
 
+// ------------------------------------------------------------------ packed fp32x2 helpers (FFMA2 / FADD2)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add_rm(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// 2^x for a packed pair on the FMA pipe: floor via round-to-minus-inf magic add, degree-3 minimax
+// polynomial of 2^f on [0,1), exponent spliced in with integer shift+add. x <= 127 is guaranteed by
+// the caller (x <= AT_RESCALE_THRESHOLD); x is clamped at -127 from below.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x0 = fmaxf(x0, -127.0f);
+  x1 = fmaxf(x1, -127.0f);
+  const uint64_t xc = f2_pack(x0, x1);
+  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);                 // 2^23 + 2^22
+  const uint64_t xr = f2_add_rm(xc, magic);                                  // low mantissa bits = floor(x)
+  const uint64_t fl = f2_sub(xr, magic);
+  const uint64_t fr = f2_sub(xc, fl);                                        // in [0, 1)
+  uint64_t acc = f2_fma(fr, f2_pack(0.077119089663028717f, 0.077119089663028717f),
+                        f2_pack(0.227564394474029541f, 0.227564394474029541f));
+  acc = f2_fma(acc, fr, f2_pack(0.695146143436431885f, 0.695146143436431885f));
+  acc = f2_fma(acc, fr, f2_pack(1.0f, 1.0f));
+  float r0, r1, q0, q1;
+  f2_unpack(xr, r0, r1);
+  f2_unpack(acc, q0, q1);
+  p0 = __int_as_float((__float_as_int(r0) << 23) + __float_as_int(q0));
+  p1 = __int_as_float((__float_as_int(r1) << 23) + __float_as_int(q1));
+}
+
+// NPOLY of the 64 column pairs of a row take the polynomial path, spread evenly.
+template <int NPOLY>
+__host__ __device__ constexpr bool pair_uses_poly(int pi) {
+  return ((pi + 1) * NPOLY) / 64 != (pi * NPOLY) / 64;
+}
+
+// exp2 of NPAIRS column pairs starting at pair PAIR0 of the row (for the poly pattern) held in s[2*i], s[2*i+1];
+// packs P as bf16x2 into pk[i] and accumulates the row sum into l2a/l2b.
+template <int NPOLY, int PAIR0, int NPAIRS>
+__device__ __forceinline__ void exp_pairs(const uint32_t* s, uint32_t* pk, uint64_t sc2, uint64_t negm2,
+                                          uint64_t& l2a, uint64_t& l2b) {
+#pragma unroll
+  for (int i = 0; i < NPAIRS; ++i) {
+    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, negm2);
+    float p0, p1;
+    if (pair_uses_poly<NPOLY>(PAIR0 + i)) {
+      ex2_poly2(x2, p0, p1);
+    } else {
+      float x0, x1;
+      f2_unpack(x2, x0, x1);
+      p0 = ptx::ex2_approx(x0);
+      p1 = ptx::ex2_approx(x1);
+    }
+    if (i & 1) l2b = f2_add(l2b, f2_pack(p0, p1)); else l2a = f2_add(l2a, f2_pack(p0, p1));
+    pk[i] = pack_bf16x2(p0, p1);
+  }
+}
+
+__device__ __forceinline__ float max64(const uint32_t (&s)[64]) {
+  float mx0 = max3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+  float mx1 = max3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
+  float mx2 = max3(__uint_as_float(s[6]), __uint_as_float(s[7]), __uint_as_float(s[8]));
+  float mx3 = max3(__uint_as_float(s[9]), __uint_as_float(s[10]), __uint_as_float(s[11]));
+#pragma unroll
+  for (int i = 12; i < 60; i += 8) {
+    mx0 = max3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+    mx1 = max3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+    mx2 = max3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+    mx3 = max3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+  }
+  mx0 = max3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
+  mx1 = max3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
+  return fmaxf(max3(mx0, mx1, mx2), mx3);
+}
+
+// TMEM columns: S_t [t*128, t*128+128)   P_t half hh [256 + t*64 + hh*32, +32) (bf16 pairs)   O_t [384 + t*64, +64)
+constexpr uint32_t AT_COL_P = 256;
+constexpr uint32_t AT_COL_O = 384;
+
+template <int NPOLY>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, AttnParams prm) {
@@ -51,15 +171,15 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + 2 * AT_TILE_BYTES;
-  uint8_t* sP = sKV + AT_KV_SLOTS * AT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AT_KV_SLOTS * AT_TILE_BYTES);
   uint64_t* q_full = bars;                        // 1
   uint64_t* kv_full = bars + 1;                   // AT_KV_SLOTS
   uint64_t* kv_empty = kv_full + AT_KV_SLOTS;     // AT_KV_SLOTS
-  uint64_t* s_full = kv_empty + AT_KV_SLOTS;      // 2
-  uint64_t* p_ready = s_full + 2;                 // 2
-  uint64_t* o_final = p_ready + 2;                // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+  uint64_t* s_full = kv_empty + AT_KV_SLOTS;      // [2]    S_t(j) is in TMEM
+  uint64_t* s_free = s_full + 2;                  // [2]    every softmax thread of tile t holds its S row in registers
+  uint64_t* p_ready = s_free + 2;                 // [2][2] P_t(j, half) is in TMEM
+  uint64_t* pv_done = p_ready + 4;                // [2][2] O_t += P_t(j, half) V_j(half) has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,8 +200,11 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_free[i], 128);
+    }
+    for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&p_ready[i], 128);
-      ptx::mbar_init(&o_final[i], 1);
+      ptx::mbar_init(&pv_done[i], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -96,6 +219,7 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (wg == 0) {
     ptx::setmaxnreg_dec<56>();
+    // Ring order of the 16 KB tiles: K_0, then for every j: K_{j+1} (if any), V_j.
     if (warp == 0) {
       // ---------------------------------------------------------- TMA producer
       if (lane == 0) {
@@ -104,140 +228,158 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         ptx::tma_load_3d(sQ + AT_TILE_BYTES, &tmQ, q_full, head * AT_D, m0 + AT_BM, batch);
         int slot = 0;
         uint32_t phase = 0;
+        auto load = [&](const CUtensorMap* tm, int row0) {
+          ptx::mbar_wait(&kv_empty[slot], phase ^ 1);
+          ptx::mbar_expect_tx(&kv_full[slot], AT_TILE_BYTES);
+          ptx::tma_load_3d(sKV + slot * AT_TILE_BYTES, tm, &kv_full[slot], head * AT_D, row0, batch);
+          if (++slot == AT_KV_SLOTS) { slot = 0; phase ^= 1; }
+        };
+        load(&tmK, 0);
         for (int j = 0; j < nkv; ++j) {
-#pragma unroll
-          for (int kv = 0; kv < 2; ++kv) {
-            ptx::mbar_wait(&kv_empty[slot], phase ^ 1);
-            ptx::mbar_expect_tx(&kv_full[slot], AT_TILE_BYTES);
-            ptx::tma_load_3d(sKV + slot * AT_TILE_BYTES, kv == 0 ? &tmK : &tmV, &kv_full[slot],
-                             head * AT_D, j * AT_BN, batch);
-            if (++slot == AT_KV_SLOTS) { slot = 0; phase ^= 1; }
-          }
+          if (j + 1 < nkv) load(&tmK, (j + 1) * AT_BN);
+          load(&tmV, j * AT_BN);
         }
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------- tcgen05 issuer
       constexpr uint32_t idesc_s = ptx::idesc_bf16(AT_BM, AT_BN, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = ptx::idesc_bf16(AT_BM, AT_D, 0, 1);   // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_o = ptx::idesc_bf16(AT_BM, AT_D, 0, 1);   // P (TMEM) x V (MN-major)
       const uint32_t sQ_a = ptx::smem_u32(sQ);
       const uint32_t sKV_a = ptx::smem_u32(sKV);
-      const uint32_t sP_a = ptx::smem_u32(sP);
-      int slot = 0;
-      uint32_t phase = 0;
-      auto issue_s = [&](int t, int kslot) {
-        if (lane == 0) {
+      // Event-driven issue: each Q tile t walks the fixed sequence
+      //   s_free(j) -> S_t(j+1);  p_ready(j,0) -> PV_t(j,0);  p_ready(j,1) -> PV_t(j,1);  j += 1
+      // and the issuer serves whichever tile's next event has fired, so the two softmax warpgroups may
+      // run at any phase offset (they are started a fraction of a period apart so that their MUFU-idle
+      // windows do not coincide).
+      if (lane == 0) {
+        // position of a tile in the ring sequence K_0, K_1, V_0, K_2, V_1, ..., K_{n-1}, V_{n-2}, V_{n-1}
+        auto idx_k = [&](int j) { return j == 0 ? 0 : 2 * j - 1; };
+        auto idx_v = [&](int j) { return j < nkv - 1 ? 2 * j + 2 : 2 * nkv - 1; };
+        auto kv_ready = [&](int idx) { return ptx::mbar_test_wait(&kv_full[idx % AT_KV_SLOTS], (idx / AT_KV_SLOTS) & 1); };
+        auto kv_release = [&](int idx) { ptx::umma_commit(&kv_empty[idx % AT_KV_SLOTS]); };
+        auto do_s = [&](int t, int idx) {
           const uint64_t a = ptx::smem_desc_sw128(sQ_a + t * AT_TILE_BYTES, 16, 1024);
-          const uint64_t b = ptx::smem_desc_sw128(sKV_a + kslot * AT_TILE_BYTES, 16, 1024);
+          const uint64_t b = ptx::smem_desc_sw128(sKV_a + (idx % AT_KV_SLOTS) * AT_TILE_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < AT_D / 16; ++k)
             ptx::umma_ss(tmem_base + t * AT_BN, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
           ptx::umma_commit(&s_full[t]);
-        }
-        __syncwarp();
-      };
-      auto issue_pv = [&](int t, int vslot, bool accumulate) {
-        if (lane == 0) {
+        };
+        auto do_pv = [&](int t, int hh, int idx, bool first) {
 #pragma unroll
-          for (int k = 0; k < AT_BN / 16; ++k) {
-            const uint64_t a = ptx::smem_desc_sw128(
-                sP_a + t * AT_P_BYTES + (k >> 2) * (AT_BM * 128) + (k & 3) * 32, 16, 1024);
-            const uint64_t b = ptx::smem_desc_sw128(sKV_a + vslot * AT_TILE_BYTES + k * 2048, 1024, 1024);
-            ptx::umma_ss(tmem_base + 2 * AT_BN + t * AT_D, a, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t b = ptx::smem_desc_sw128(sKV_a + (idx % AT_KV_SLOTS) * AT_TILE_BYTES + (hh * 4 + kk) * 2048, 1024, 1024);
+            ptx::umma_ts(tmem_base + AT_COL_O + t * AT_D, tmem_base + AT_COL_P + t * 64 + hh * 32 + kk * 8, b, idesc_o,
+                         (first && kk == 0) ? 0u : 1u);
           }
-        }
-        __syncwarp();
-      };
-      auto advance = [&]() { if (++slot == AT_KV_SLOTS) { slot = 0; phase ^= 1; } };
-
-      ptx::mbar_wait(q_full, 0);
-      // prologue: S_0(0), S_1(0)
-      ptx::mbar_wait(&kv_full[slot], phase);
-      ptx::tc_fence_after();
-      issue_s(0, slot);
-      issue_s(1, slot);
-      if (lane == 0) ptx::umma_commit(&kv_empty[slot]);
-      __syncwarp();
-      advance();
-      for (int j = 0; j < nkv; ++j) {
-        const int vslot = slot;
-        const uint32_t vphase = phase;
-        advance();
-        const int kslot = slot;          // K_{j+1}
-        const uint32_t kphase = phase;
-        const bool more = (j + 1 < nkv);
-        if (more) advance();
-        ptx::mbar_wait(&kv_full[vslot], vphase);
+          ptx::umma_commit(&pv_done[t * 2 + hh]);
+        };
+        ptx::mbar_wait(q_full, 0);
+        ptx::mbar_wait(&kv_full[0], 0);
+        ptx::tc_fence_after();
+        do_s(0, 0);
+        do_s(1, 0);
+        kv_release(0);
+        if (prm.issuer_mode == 0) {
+          // fixed order (both warpgroups roughly in phase): S_0(j+1), S_1(j+1), then the four PV groups
+          for (int j = 0; j < nkv; ++j) {
+            if (j + 1 < nkv) {
+              while (!kv_ready(idx_k(j + 1))) {
+              }
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          ptx::mbar_wait(&p_ready[t], j & 1);
-          ptx::tc_fence_after();
-          issue_pv(t, vslot, j > 0);
-          if (lane == 0) {
-            if (t == 1) ptx::umma_commit(&kv_empty[vslot]);
-            if (!more) ptx::umma_commit(&o_final[t]);
+              for (int t = 0; t < 2; ++t) {
+                ptx::mbar_wait(&s_free[t], j & 1);
+                ptx::tc_fence_after();
+                do_s(t, idx_k(j + 1));
+              }
+              kv_release(idx_k(j + 1));
+            }
+            ptx::mbar_wait(&kv_full[idx_v(j) % AT_KV_SLOTS], (idx_v(j) / AT_KV_SLOTS) & 1);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                ptx::mbar_wait(&p_ready[t * 2 + hh], j & 1);
+                ptx::tc_fence_after();
+                do_pv(t, hh, idx_v(j), j == 0 && hh == 0);
+              }
+            }
+            kv_release(idx_v(j));
           }
-          __syncwarp();
-          if (more) {
-            if (t == 0) {
-              ptx::mbar_wait(&kv_full[kslot], kphase);
+        } else {
+        int jj[2] = {0, 0};       // current kv tile of each Q tile
+        int st[2] = {0, 0};       // 0: waiting s_free(j)   1: waiting p_ready(j,0)   2: waiting p_ready(j,1)
+        int s_issued[2] = {0, 0}; // highest j for which S_t(j) has been issued
+        int pv_issued[2] = {-1, -1};
+        int live = 2;
+        while (live > 0) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int j = jj[t];
+            if (j >= nkv) continue;
+            if (st[t] == 0) {
+              if (j + 1 >= nkv) { st[t] = 1; continue; }
+              if (!ptx::mbar_test_wait(&s_free[t], j & 1) || !kv_ready(idx_k(j + 1))) continue;
               ptx::tc_fence_after();
-            }
-            issue_s(t, kslot);
-            if (t == 1) {
-              if (lane == 0) ptx::umma_commit(&kv_empty[kslot]);
-              __syncwarp();
+              do_s(t, idx_k(j + 1));
+              s_issued[t] = j + 1;
+              if (s_issued[t ^ 1] >= j + 1) kv_release(idx_k(j + 1));
+              st[t] = 1;
+            } else {
+              const int hh = st[t] - 1;
+              if (!ptx::mbar_test_wait(&p_ready[t * 2 + hh], j & 1) || !kv_ready(idx_v(j))) continue;
+              ptx::tc_fence_after();
+              do_pv(t, hh, idx_v(j), j == 0 && hh == 0);
+              if (hh == 0) {
+                st[t] = 2;
+              } else {
+                pv_issued[t] = j;
+                if (pv_issued[t ^ 1] >= j) kv_release(idx_v(j));
+                st[t] = 0;
+                jj[t] = j + 1;
+                if (j + 1 >= nkv) --live;
+              }
             }
           }
+        }
         }
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ softmax warpgroups
-    ptx::setmaxnreg_inc<216>();
+    ptx::setmaxnreg_inc<224>();
     const int t = wg - 1;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // row inside the Q tile
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + t * AT_BN;
-    const uint32_t tO = tmem_base + lane_addr + 2 * AT_BN + t * AT_D;
-    const uint32_t p_row = ptx::smem_u32(sP) + t * AT_P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-    const uint32_t xr = r & 7;
+    const uint32_t tP = tmem_base + lane_addr + AT_COL_P + t * 64;
+    const uint32_t tO = tmem_base + lane_addr + AT_COL_O + t * AT_D;
     const float sc = prm.scale_log2;
+    const uint64_t sc2 = f2_pack(sc, sc);
     const int tail = prm.Skv - (nkv - 1) * AT_BN;            // valid kv rows in the last tile
     float m_used = -INFINITY;
-    float l = 0.f;
+    uint64_t l2a = f2_pack(0.f, 0.f), l2b = l2a;             // 4 partial row sums
 
-    for (int j = 0; j < nkv; ++j) {
-      ptx::mbar_wait(&s_full[t], j & 1);
-      ptx::tc_fence_after();
-      uint32_t s[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32(tS + c * 32, s[c]);
-      ptx::tmem_ld_wait();
-      if (j == nkv - 1 && tail < AT_BN) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= tail) s[c][i] = 0xff800000u;  // -inf
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[0][i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[1][i]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[2][i]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[3][i]));
-      }
-      const float m_cur = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
-      const bool need = m_cur > m_used + AT_RESCALE_THRESHOLD;
+    uint32_t sa[64], sb[64];                                 // S row: columns [0,64) and [64,128)
+
+    // Lazy rescale: the exponent offset m_used only moves when a half-row max exceeds it by 2^8.
+    // hh-th half of tile j; O_t is quiescent once the previous PV of this tile has completed.
+    auto maybe_rescale = [&](float hmax, int j, int hh) {
+      const bool need = hmax * sc > m_used + AT_RESCALE_THRESHOLD;
       if (__any_sync(0xffffffffu, need)) {
-        const float m_new = fmaxf(m_used, m_cur);
-        const float factor = ptx::ex2_approx(m_used - m_new);   // j == 0: exp2(-inf) = 0
+        const float m_new = fmaxf(m_used, hmax * sc);
+        const float factor = ptx::ex2_approx(m_used - m_new);   // first half of all: exp2(-inf) = 0
         m_used = m_new;
-        l *= factor;
-        if (j > 0) {
-          // s_full(j) was committed after PV(j-1) on the same issuing thread, so O is quiescent here
+        const uint64_t f2 = f2_pack(factor, factor);
+        const uint64_t z2 = f2_pack(0.f, 0.f);
+        l2a = f2_fma(l2a, f2, z2);
+        l2b = f2_fma(l2b, f2, z2);
+        if (j > 0 || hh > 0) {
+          if (hh == 0) ptx::mbar_wait(&pv_done[t * 2 + 1], (j - 1) & 1);
+          else ptx::mbar_wait(&pv_done[t * 2 + 0], j & 1);
+          ptx::tc_fence_after();
 #pragma unroll
           for (int c = 0; c < AT_D / 16; ++c) {
             uint32_t o[16];
@@ -250,35 +392,82 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           ptx::tmem_st_wait();
         }
       }
-      const float neg_m = -m_used;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            p[i] = ptx::ex2_approx(fmaf(__uint_as_float(s[c][g * 8 + i]), sc, neg_m));
-          l0 += p[0] + p[4];
-          l1 += p[1] + p[5];
-          l2 += p[2] + p[6];
-          l3 += p[3] + p[7];
-          const int chunk = c * 4 + g;                     // 16-byte chunk index along the row (0..15)
-          const uint32_t addr = p_row + (chunk >> 3) * (AT_BM * 128) + (((chunk & 7) ^ xr) << 4);
-          ptx::st_shared_v4(addr, pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
-                            pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-        }
-      }
-      l += (l0 + l1) + (l2 + l3);
-      ptx::fence_proxy_async_smem();
+    };
+    auto publish_p = [&](const uint32_t (&pk)[32], int hh) {
+      ptx::tmem_st_32x32(tP + hh * 32, pk);
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&p_ready[t]);
+      ptx::mbar_arrive(&p_ready[t * 2 + hh]);
+    };
+
+    if (t == 1 && prm.stagger_cycles > 0) {                   // start the second warpgroup a fraction of a period late
+      const long long t0 = clock64();
+      while (clock64() - t0 < prm.stagger_cycles) {
+      }
+    }
+    ptx::mbar_wait(&s_full[t], 0);
+    ptx::tc_fence_after();
+    ptx::tmem_ld_32x32(tS, *reinterpret_cast<uint32_t (*)[32]>(&sa[0]));
+    ptx::tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t (*)[32]>(&sa[32]));
+    ptx::tmem_ld_wait();
+
+    for (int j = 0; j < nkv; ++j) {
+      const bool last = (j == nkv - 1);
+      // ---- half 0 (columns [0,64) in sa); the second half of S_t(j) streams into sb meanwhile
+      ptx::tmem_ld_32x32(tS + 64, *reinterpret_cast<uint32_t (*)[32]>(&sb[0]));
+      ptx::tmem_ld_32x32(tS + 96, *reinterpret_cast<uint32_t (*)[32]>(&sb[32]));
+      if (last && tail < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= tail) sa[i] = 0xff800000u;  // -inf
+      }
+      const float hmax0 = max64(sa);                         // ALU work that overlaps the TMEM load latency of sb
+      ptx::tmem_ld_wait();                                   // sb has landed: S_t(j) is fully in registers
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_free[t]);                          // S_t(j+1) may now overwrite the TMEM tile
+      maybe_rescale(hmax0, j, 0);
+      uint32_t pk[32];
+      {
+        const uint64_t negm2 = f2_pack(-m_used, -m_used);
+        exp_pairs<NPOLY, 0, 32>(&sa[0], &pk[0], sc2, negm2, l2a, l2b);
+      }
+      if (j > 0) {                                           // P_t(j-1, 0) has been consumed
+        ptx::mbar_wait(&pv_done[t * 2 + 0], (j - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      publish_p(pk, 0);
+      // ---- half 1 (columns [64,128) in sb); the first half of S_t(j+1) streams into sa meanwhile
+      if (!last) {
+        ptx::mbar_wait(&s_full[t], (j + 1) & 1);
+        ptx::tc_fence_after();
+        ptx::tmem_ld_32x32(tS, *reinterpret_cast<uint32_t (*)[32]>(&sa[0]));
+        ptx::tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t (*)[32]>(&sa[32]));
+      }
+      if (last && tail < AT_BN) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (64 + i >= tail) sb[i] = 0xff800000u;
+      }
+      maybe_rescale(max64(sb), j, 1);
+      {
+        const uint64_t negm2 = f2_pack(-m_used, -m_used);
+        exp_pairs<NPOLY, 32, 32>(&sb[0], &pk[0], sc2, negm2, l2a, l2b);
+      }
+      if (j > 0) {
+        ptx::mbar_wait(&pv_done[t * 2 + 1], (j - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      publish_p(pk, 1);
+      ptx::tmem_ld_wait();                                   // sa = first half of S_t(j+1)
     }
 
     // ---------------------------------------------------------- epilogue: O / l -> bf16 global
-    ptx::mbar_wait(&o_final[t], 0);
+    ptx::mbar_wait(&pv_done[t * 2 + 1], (nkv - 1) & 1);
     ptx::tc_fence_after();
+    float la, lb, lc, ld;
+    f2_unpack(l2a, la, lb);
+    f2_unpack(l2b, lc, ld);
+    const float l = (la + lb) + (lc + ld);
     const int row = m0 + t * AT_BM + r;
     const float inv_l = 1.0f / l;
     __nv_bfloat16* orow = prm.out + static_cast<long long>(batch) * prm.out_batch_stride +
@@ -307,6 +496,19 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, AT_TMEM_COLS);
+}
+
+template <int NPOLY>
+int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm, dim3 grid,
+                cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VGPA_CUDA(cudaFuncSetAttribute(attn_fwd_d64_kernel<NPOLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    attr_set = true;
+  }
+  attn_fwd_d64_kernel<NPOLY><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tq, tk, tv, prm);
+  VGPA_LAUNCH_CHECK("attn_fwd_d64_kernel");
+  return 0;
 }
 
 }  // namespace
@@ -346,11 +548,6 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
     const uint64_t str[2] = {(uint64_t)a->v_row_stride * 2, (uint64_t)a->v_batch_stride * 2};
     if (int rc = make_tmap_bf16(&tv, a->v, 3, dims, str, box)) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    VGPA_CUDA(cudaFuncSetAttribute(attn_fwd_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    attr_set = true;
-  }
   AttnParams prm;
   prm.out = static_cast<__nv_bfloat16*>(a->out);
   prm.out_row_stride = a->out_row_stride;
@@ -360,7 +557,24 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
   const float scale = a->scale > 0.f ? a->scale : 0.125f;
   prm.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((a->Sq + 2 * AT_BM - 1) / (2 * AT_BM), a->H, a->B);
-  attn_fwd_d64_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, prm);
-  VGPA_LAUNCH_CHECK("attn_fwd_d64_kernel");
-  return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // Tuning knob (development only): share of exponentials evaluated on the FMA pipe, in 64ths.
+  static int npoly = -1, stagger = 0;
+  if (npoly < 0) {
+    const char* e = getenv("VGPA_ATTN_NPOLY");
+    npoly = e ? atoi(e) : 0;
+    const char* g = getenv("VGPA_ATTN_STAGGER");
+    stagger = g ? atoi(g) : 600;
+  }
+  static int issuer = -1;
+  if (issuer < 0) { const char* e = getenv("VGPA_ATTN_ISSUER"); issuer = e ? atoi(e) : 0; }
+  prm.stagger_cycles = stagger;
+  prm.issuer_mode = issuer;
+  switch (npoly) {
+    case 0: return launch_attn<0>(tq, tk, tv, prm, grid, s);
+    case 16: return launch_attn<16>(tq, tk, tv, prm, grid, s);
+    case 32: return launch_attn<32>(tq, tk, tv, prm, grid, s);
+    case 40: return launch_attn<40>(tq, tk, tv, prm, grid, s);
+    default: return launch_attn<24>(tq, tk, tv, prm, grid, s);
+  }
 }

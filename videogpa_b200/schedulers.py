@@ -88,7 +88,8 @@ class CogVideoXDPMScheduler(_Base):
     `generator` every step (one randn of the latent shape), in step order."""
 
     def _lam(self, a):
-        return math.log((a / (1 - a)) ** 0.5)
+        # zero-terminal-SNR makes alphas_cumprod[999] exactly 0: lambda = -inf there (torch's log(0) in diffusers)
+        return -math.inf if a <= 0.0 else math.log((a / (1 - a)) ** 0.5)
 
     def coefficients(self, t: int, t_back):
         ac = self.alphas_cumprod
