@@ -156,3 +156,14 @@ def test_world_size_2_gloo(tmp_path):
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("worker ok") == 2
+
+
+def test_frame_and_pair_index_rules_match_oracle():
+    """a-17: the bit-exact index rules of the host mirror against the oracle restatement and the SURVEY KAT."""
+    from oracle import scorer_np as o
+    from videogpa_b200.metrics import consecutive_pairs, sample_frame_indices
+    assert sample_frame_indices(49, 10).tolist() == [0, 5, 10, 16, 21, 26, 32, 37, 42, 48]
+    for total, n in [(49, 10), (6, 10), (1, 10), (81, 10), (120, 8), (10, 10)]:
+        assert sample_frame_indices(total, n).tolist() == o.uniform_frame_indices(total, n).tolist()
+    assert consecutive_pairs(4) == list(o.consecutive_pairs(4)) == [(0, 1), (1, 2), (2, 3)]
+    assert consecutive_pairs(1) == []

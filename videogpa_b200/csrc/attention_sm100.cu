@@ -51,8 +51,6 @@ struct AttnParams {
   long long out_batch_stride;
   int Sq, Skv;
   float scale_log2;
-  int stagger_cycles;
-  int issuer_mode;
 };
 
 // ------------------------------------------------------------------ packed fp32x2 helpers (FFMA2 / FADD2)
@@ -222,7 +220,7 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // Ring order of the 16 KB tiles: K_0, then for every j: K_{j+1} (if any), V_j.
     if (warp == 0) {
       // ---------------------------------------------------------- TMA producer
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(q_full, 2 * AT_TILE_BYTES);
         ptx::tma_load_3d(sQ, &tmQ, q_full, head * AT_D, m0, batch);
         ptx::tma_load_3d(sQ + AT_TILE_BYTES, &tmQ, q_full, head * AT_D, m0 + AT_BM, batch);
@@ -246,16 +244,10 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idesc_o = ptx::idesc_bf16(AT_BM, AT_D, 0, 1);   // P (TMEM) x V (MN-major)
       const uint32_t sQ_a = ptx::smem_u32(sQ);
       const uint32_t sKV_a = ptx::smem_u32(sKV);
-      // Event-driven issue: each Q tile t walks the fixed sequence
-      //   s_free(j) -> S_t(j+1);  p_ready(j,0) -> PV_t(j,0);  p_ready(j,1) -> PV_t(j,1);  j += 1
-      // and the issuer serves whichever tile's next event has fired, so the two softmax warpgroups may
-      // run at any phase offset (they are started a fraction of a period apart so that their MUFU-idle
-      // windows do not coincide).
-      if (lane == 0) {
+      if (ptx::elect_one()) {   // elect.sync: the compiler then issues tcgen05 ops without a per-lane waterfall loop
         // position of a tile in the ring sequence K_0, K_1, V_0, K_2, V_1, ..., K_{n-1}, V_{n-2}, V_{n-1}
         auto idx_k = [&](int j) { return j == 0 ? 0 : 2 * j - 1; };
         auto idx_v = [&](int j) { return j < nkv - 1 ? 2 * j + 2 : 2 * nkv - 1; };
-        auto kv_ready = [&](int idx) { return ptx::mbar_test_wait(&kv_full[idx % AT_KV_SLOTS], (idx / AT_KV_SLOTS) & 1); };
         auto kv_release = [&](int idx) { ptx::umma_commit(&kv_empty[idx % AT_KV_SLOTS]); };
         auto do_s = [&](int t, int idx) {
           const uint64_t a = ptx::smem_desc_sw128(sQ_a + t * AT_TILE_BYTES, 16, 1024);
@@ -280,68 +272,33 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         do_s(0, 0);
         do_s(1, 0);
         kv_release(0);
-        if (prm.issuer_mode == 0) {
-          // fixed order (both warpgroups roughly in phase): S_0(j+1), S_1(j+1), then the four PV groups
+        {
+          // Anti-phase order: warpgroup 1 is held about half a kv tile behind warpgroup 0 (its S tile is only
+          // issued after warpgroup 0 has published its first P half), so the MUFU-idle windows of the two
+          // warps that share an SM sub-partition (tile boundary, waits) never coincide.
+          auto wait_kv = [&](int idx) { ptx::mbar_wait(&kv_full[idx % AT_KV_SLOTS], (idx / AT_KV_SLOTS) & 1); };
+          auto pv = [&](int t, int hh, int j) {
+            ptx::mbar_wait(&p_ready[t * 2 + hh], j & 1);
+            ptx::tc_fence_after();
+            do_pv(t, hh, idx_v(j), j == 0 && hh == 0);
+          };
+          auto sq = [&](int t, int j) {   // S_t(j+1)
+            ptx::mbar_wait(&s_free[t], j & 1);
+            ptx::tc_fence_after();
+            do_s(t, idx_k(j + 1));
+          };
           for (int j = 0; j < nkv; ++j) {
-            if (j + 1 < nkv) {
-              while (!kv_ready(idx_k(j + 1))) {
-              }
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                ptx::mbar_wait(&s_free[t], j & 1);
-                ptx::tc_fence_after();
-                do_s(t, idx_k(j + 1));
-              }
-              kv_release(idx_k(j + 1));
-            }
-            ptx::mbar_wait(&kv_full[idx_v(j) % AT_KV_SLOTS], (idx_v(j) / AT_KV_SLOTS) & 1);
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                ptx::mbar_wait(&p_ready[t * 2 + hh], j & 1);
-                ptx::tc_fence_after();
-                do_pv(t, hh, idx_v(j), j == 0 && hh == 0);
-              }
-            }
-            kv_release(idx_v(j));
+            if (j > 0) pv(0, 1, j - 1);
+            if (j + 1 < nkv) { wait_kv(idx_k(j + 1)); sq(0, j); }
+            wait_kv(idx_v(j));
+            pv(0, 0, j);
+            if (j > 0) { pv(1, 1, j - 1); kv_release(idx_v(j - 1)); }
+            if (j + 1 < nkv) { sq(1, j); kv_release(idx_k(j + 1)); }
+            pv(1, 0, j);
           }
-        } else {
-        int jj[2] = {0, 0};       // current kv tile of each Q tile
-        int st[2] = {0, 0};       // 0: waiting s_free(j)   1: waiting p_ready(j,0)   2: waiting p_ready(j,1)
-        int s_issued[2] = {0, 0}; // highest j for which S_t(j) has been issued
-        int pv_issued[2] = {-1, -1};
-        int live = 2;
-        while (live > 0) {
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int j = jj[t];
-            if (j >= nkv) continue;
-            if (st[t] == 0) {
-              if (j + 1 >= nkv) { st[t] = 1; continue; }
-              if (!ptx::mbar_test_wait(&s_free[t], j & 1) || !kv_ready(idx_k(j + 1))) continue;
-              ptx::tc_fence_after();
-              do_s(t, idx_k(j + 1));
-              s_issued[t] = j + 1;
-              if (s_issued[t ^ 1] >= j + 1) kv_release(idx_k(j + 1));
-              st[t] = 1;
-            } else {
-              const int hh = st[t] - 1;
-              if (!ptx::mbar_test_wait(&p_ready[t * 2 + hh], j & 1) || !kv_ready(idx_v(j))) continue;
-              ptx::tc_fence_after();
-              do_pv(t, hh, idx_v(j), j == 0 && hh == 0);
-              if (hh == 0) {
-                st[t] = 2;
-              } else {
-                pv_issued[t] = j;
-                if (pv_issued[t ^ 1] >= j) kv_release(idx_v(j));
-                st[t] = 0;
-                jj[t] = j + 1;
-                if (j + 1 >= nkv) --live;
-              }
-            }
-          }
-        }
+          pv(0, 1, nkv - 1);
+          pv(1, 1, nkv - 1);
+          kv_release(idx_v(nkv - 1));
         }
       }
       __syncwarp();
@@ -365,10 +322,22 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t sa[64], sb[64];                                 // S row: columns [0,64) and [64,128)
 
     // Lazy rescale: the exponent offset m_used only moves when a half-row max exceeds it by 2^8.
-    // hh-th half of tile j; O_t is quiescent once the previous PV of this tile has completed.
-    auto maybe_rescale = [&](float hmax, int j, int hh) {
+    // P_t(j, hh) is stored to TMEM right after its exponentials, but the wait::st + p_ready arrive is
+    // deferred into the next half's instruction stream so the store latency hides behind MUFU work.
+    bool pend = false;                                        // a P store of this thread awaits publication
+    int pend_hh = 0;
+    auto publish_pending = [&]() {
+      if (pend) {
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&p_ready[t * 2 + pend_hh]);
+        pend = false;
+      }
+    };
+    auto rescale_check = [&](float hmax, int j, int hh) {
       const bool need = hmax * sc > m_used + AT_RESCALE_THRESHOLD;
       if (__any_sync(0xffffffffu, need)) {
+        publish_pending();                                    // the PV we are about to wait for may need it
         const float m_new = fmaxf(m_used, hmax * sc);
         const float factor = ptx::ex2_approx(m_used - m_new);   // first half of all: exp2(-inf) = 0
         m_used = m_new;
@@ -393,73 +362,72 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     };
-    auto publish_p = [&](const uint32_t (&pk)[32], int hh) {
-      ptx::tmem_st_32x32(tP + hh * 32, pk);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&p_ready[t * 2 + hh]);
+    auto mask_tail = [&](uint32_t (&v)[64], int col0) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        if (col0 + i >= tail) v[i] = 0xff800000u;  // -inf
     };
 
-    if (t == 1 && prm.stagger_cycles > 0) {                   // start the second warpgroup a fraction of a period late
-      const long long t0 = clock64();
-      while (clock64() - t0 < prm.stagger_cycles) {
-      }
-    }
     ptx::mbar_wait(&s_full[t], 0);
     ptx::tc_fence_after();
     ptx::tmem_ld_32x32(tS, *reinterpret_cast<uint32_t (*)[32]>(&sa[0]));
     ptx::tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t (*)[32]>(&sa[32]));
     ptx::tmem_ld_wait();
+    if (nkv == 1 && tail < 64) mask_tail(sa, 0);
+    float hmax_a = max64(sa);
+    uint32_t pk[32];
 
     for (int j = 0; j < nkv; ++j) {
       const bool last = (j == nkv - 1);
-      // ---- half 0 (columns [0,64) in sa); the second half of S_t(j) streams into sb meanwhile
+      // ================= half 0: columns [0,64) are in sa; [64,128) stream into sb meanwhile
       ptx::tmem_ld_32x32(tS + 64, *reinterpret_cast<uint32_t (*)[32]>(&sb[0]));
       ptx::tmem_ld_32x32(tS + 96, *reinterpret_cast<uint32_t (*)[32]>(&sb[32]));
-      if (last && tail < 64) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= tail) sa[i] = 0xff800000u;  // -inf
-      }
-      const float hmax0 = max64(sa);                         // ALU work that overlaps the TMEM load latency of sb
-      ptx::tmem_ld_wait();                                   // sb has landed: S_t(j) is fully in registers
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&s_free[t]);                          // S_t(j+1) may now overwrite the TMEM tile
-      maybe_rescale(hmax0, j, 0);
-      uint32_t pk[32];
+      rescale_check(hmax_a, j, 0);
+      float hmax_b;
       {
         const uint64_t negm2 = f2_pack(-m_used, -m_used);
-        exp_pairs<NPOLY, 0, 32>(&sa[0], &pk[0], sc2, negm2, l2a, l2b);
+        exp_pairs<NPOLY, 0, 16>(&sa[0], &pk[0], sc2, negm2, l2a, l2b);
+        publish_pending();                                   // P_t(j-1, 1)
+        ptx::tmem_ld_wait();                                 // sb has landed: S_t(j) is fully in registers
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&s_free[t]);                        // S_t(j+1) may now overwrite the TMEM tile
+        if (last && tail < AT_BN) mask_tail(sb, 64);
+        hmax_b = max64(sb);
+        exp_pairs<NPOLY, 16, 16>(&sa[32], &pk[16], sc2, negm2, l2a, l2b);
       }
       if (j > 0) {                                           // P_t(j-1, 0) has been consumed
         ptx::mbar_wait(&pv_done[t * 2 + 0], (j - 1) & 1);
         ptx::tc_fence_after();
       }
-      publish_p(pk, 0);
-      // ---- half 1 (columns [64,128) in sb); the first half of S_t(j+1) streams into sa meanwhile
-      if (!last) {
-        ptx::mbar_wait(&s_full[t], (j + 1) & 1);
-        ptx::tc_fence_after();
-        ptx::tmem_ld_32x32(tS, *reinterpret_cast<uint32_t (*)[32]>(&sa[0]));
-        ptx::tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t (*)[32]>(&sa[32]));
-      }
-      if (last && tail < AT_BN) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (64 + i >= tail) sb[i] = 0xff800000u;
-      }
-      maybe_rescale(max64(sb), j, 1);
+      ptx::tmem_st_32x32(tP, pk);
+      pend = true; pend_hh = 0;
+      // ================= half 1: columns [64,128) are in sb; the first half of S_t(j+1) streams into sa
+      rescale_check(hmax_b, j, 1);
       {
         const uint64_t negm2 = f2_pack(-m_used, -m_used);
-        exp_pairs<NPOLY, 32, 32>(&sb[0], &pk[0], sc2, negm2, l2a, l2b);
+        exp_pairs<NPOLY, 32, 16>(&sb[0], &pk[0], sc2, negm2, l2a, l2b);
+        publish_pending();                                   // P_t(j, 0)
+        if (!last) {
+          ptx::mbar_wait(&s_full[t], (j + 1) & 1);
+          ptx::tc_fence_after();
+          ptx::tmem_ld_32x32(tS, *reinterpret_cast<uint32_t (*)[32]>(&sa[0]));
+          ptx::tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t (*)[32]>(&sa[32]));
+        }
+        exp_pairs<NPOLY, 48, 16>(&sb[32], &pk[16], sc2, negm2, l2a, l2b);
       }
       if (j > 0) {
         ptx::mbar_wait(&pv_done[t * 2 + 1], (j - 1) & 1);
         ptx::tc_fence_after();
       }
-      publish_p(pk, 1);
-      ptx::tmem_ld_wait();                                   // sa = first half of S_t(j+1)
+      ptx::tmem_st_32x32(tP + 32, pk);
+      pend = true; pend_hh = 1;
+      if (!last) {
+        ptx::tmem_ld_wait();                                 // sa = first half of S_t(j+1)
+        if (j + 1 == nkv - 1 && tail < 64) mask_tail(sa, 0);
+        hmax_a = max64(sa);
+      }
     }
+    publish_pending();
 
     // ---------------------------------------------------------- epilogue: O / l -> bf16 global
     ptx::mbar_wait(&pv_done[t * 2 + 1], (nkv - 1) & 1);
@@ -558,23 +526,16 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
   prm.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((a->Sq + 2 * AT_BM - 1) / (2 * AT_BM), a->H, a->B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // Tuning knob (development only): share of exponentials evaluated on the FMA pipe, in 64ths.
-  static int npoly = -1, stagger = 0;
+  // Development knob: share of the exponentials evaluated on the FMA pipe, in 64ths of a row (default 16).
+  static int npoly = -1;
   if (npoly < 0) {
     const char* e = getenv("VGPA_ATTN_NPOLY");
-    npoly = e ? atoi(e) : 0;
-    const char* g = getenv("VGPA_ATTN_STAGGER");
-    stagger = g ? atoi(g) : 600;
+    npoly = e ? atoi(e) : 16;
   }
-  static int issuer = -1;
-  if (issuer < 0) { const char* e = getenv("VGPA_ATTN_ISSUER"); issuer = e ? atoi(e) : 0; }
-  prm.stagger_cycles = stagger;
-  prm.issuer_mode = issuer;
   switch (npoly) {
     case 0: return launch_attn<0>(tq, tk, tv, prm, grid, s);
-    case 16: return launch_attn<16>(tq, tk, tv, prm, grid, s);
     case 32: return launch_attn<32>(tq, tk, tv, prm, grid, s);
-    case 40: return launch_attn<40>(tq, tk, tv, prm, grid, s);
-    default: return launch_attn<24>(tq, tk, tv, prm, grid, s);
+    case 24: return launch_attn<24>(tq, tk, tv, prm, grid, s);
+    default: return launch_attn<16>(tq, tk, tv, prm, grid, s);
   }
 }

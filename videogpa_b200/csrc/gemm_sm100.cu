@@ -235,7 +235,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {   // elect.sync keeps TMA / tcgen05 issue free of per-lane waterfall loops
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -264,7 +264,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < nk; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        if (ptx::elect_one()) {
           const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA + stage * Cfg::A_BYTES), 16, 1024);
           const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(sB + stage * Cfg::B_BYTES), 16, 1024);
 #pragma unroll

@@ -276,3 +276,16 @@ class EpipolarMetric(Metric):
         elif x.max() <= 1.0:
             x = x * 255.0
         return np.clip(x, 0, 255).astype(np.uint8)
+
+def sample_frame_indices(total_frames: int, num_frames: int):
+    """Frame-index rule of the scorer (utils/video_utils.py:31-32): `np.linspace(0, total-1, n_eff).astype(int)` with
+    n_eff = min(num_frames, total). Bit-exact part of the contract: 49 frames, n = 10 ->
+    [0, 5, 10, 16, 21, 26, 32, 37, 42, 48]."""
+    import numpy as np
+    n_eff = min(int(num_frames), int(total_frames))
+    return np.linspace(0, total_frames - 1, n_eff).astype(int)
+
+
+def consecutive_pairs(T: int):
+    """Frame pairs scored by MVCS / Epipolar: (i, i+1) (metrics/mvcs.py:59-60, metrics/epipolar.py:167-168)."""
+    return [(i, i + 1) for i in range(max(0, T - 1))]
