@@ -238,6 +238,73 @@ int vgpa_dpo_loss_forward(const vgpa_dpo_args* args, void* stream);
 int vgpa_dpo_loss_backward(const vgpa_dpo_args* args, const float* d_grad_loss, void* d_grad_win, void* d_grad_lose,
                            void* stream);
 
+
+/* ================================================================================================
+ * K4 — CogVideoX VAE decoder building blocks. Replace the cuDNN conv3d / GroupNorm / interpolate calls
+ * behind diffusers' AutoencoderKLCogVideoX.decode (CogVideoXDecoder3D, CogVideoXResnetBlock3D,
+ * CogVideoXSpatialNorm3D, CogVideoXUpsample3D, CogVideoXCausalConv3d; reference call
+ * sites generate/CogVideoX-5B.py:20-21,72-77). Activations are channels-last [T, H, W, C] bf16.
+ * ============================================================================================== */
+
+/* Causal 3-D convolution as an implicit GEMM on tcgen05 (K = KT*3*3*Cin):
+ *   out[t,h,w,co] = bias[co] + residual[t,h,w,co] + sum_{kt,kh,kw,ci} x[t+kt, h+kh-1, w+kw-1, ci] * w[co][(kt,kh,kw,ci)]
+ * x is already padded in time (KT-1 leading frames: the conv_cache or the replicated first frame, written by
+ * the caller); H/W are zero padded by the TMA unit. KT in {1, 3} (KT = 1 is the per-frame Conv2d 3x3 of
+ * CogVideoXUpsample3D); the kernel is 3x3 in space. Cin % 64 == 0. Cout_pad (rows of w) in {16, 64, 128} or a
+ * multiple of 256; only the first Cout channels are written. */
+typedef struct vgpa_conv3d_args {
+  const void* x;        /* [T + KT - 1, H, W, Cin] bf16                                              */
+  const void* w;        /* [Cout_pad, KT*9*Cin] bf16, K ordered (kt, kh, kw, ci)                      */
+  const void* bias;     /* [Cout_pad] bf16 or NULL                                                   */
+  const void* residual; /* [T, H, W, ld_res] bf16 or NULL                                            */
+  void* out;            /* [T, H, W, ldo] bf16                                                       */
+  int32_t T, H, W, Cin, Cout, Cout_pad, KT;
+  int32_t ldo, ld_res;
+} vgpa_conv3d_args;
+int vgpa_conv3d_causal_bf16(const vgpa_conv3d_args* args, void* stream);
+
+/* GroupNorm statistics over one [T, H, W, C] tensor (all of T, H, W: the statistics of one frame batch of one
+ * tile, as torch.nn.GroupNorm sees it): mean_rstd [2, groups] fp32. workspace >= vgpa_groupnorm_workspace_bytes. */
+size_t vgpa_groupnorm_workspace_bytes(int C);
+int vgpa_groupnorm_stats_bf16(const void* x, int64_t n_pixels, int C, int groups, float eps, void* workspace,
+                              size_t workspace_bytes, float* mean_rstd, void* stream);
+
+/* SpatialNorm3D apply (+ optional SiLU): out = act((x - mean_g) * rstd_g * gamma_c + beta_c) * Y[z(t,h,w), c] + Bz[z(t,h,w), c])
+ * where Y = conv_y(zq), Bz = conv_b(zq) are given at LATENT resolution [Tz, Hz, Wz, C] (pointwise convs commute
+ * with the nearest-neighbour resize) and z(t,h,w) = (tz_of_t[t], h >> shift, w >> shift). */
+typedef struct vgpa_spatialnorm_args {
+  const void* x;          /* [T, H, W, C] bf16 */
+  void* out;              /* [T, H, W, C] bf16 (may point 2 frames into a time-padded buffer) */
+  const float* mean_rstd; /* [2, groups] */
+  const void* gamma;      /* [C] bf16 */
+  const void* beta;       /* [C] bf16 */
+  const void* y_lat;      /* [Tz, Hz, Wz, >=C] bf16, pixel stride ld_lat elements */
+  const void* b_lat;      /* same layout */
+  int64_t ld_lat;
+  int32_t T, H, W, C, groups;
+  int32_t Hz, Wz, shift;
+  int32_t tz_of_t[16];    /* T <= 16 */
+  int32_t silu;
+} vgpa_spatialnorm_args;
+int vgpa_spatialnorm_apply_bf16(const vgpa_spatialnorm_args* args, void* stream);
+
+/* Nearest-neighbour upsample x2 in H and W; output frame t reads input frame t_src[t] (T_out <= 16). */
+int vgpa_upsample_nearest_bf16(const void* x, void* out, int T_out, int H, int W, int C, const int32_t* t_src_host,
+                               void* stream);
+
+/* Tiled-decode composition (AutoencoderKLCogVideoX.tiled_decode blending + crop): tiles[i*cols + j] is the decoded
+ * tile [T, th_i, tw_j, ldc] bf16 (channels-last, first 3 channels used); out [3, T, H, W] bf16. */
+typedef struct vgpa_compose_args {
+  const void* tiles[16];
+  int32_t rows, cols;
+  int32_t th[4], tw[4];           /* decoded tile heights per tile row / widths per tile column */
+  int32_t T, H, W, ldc;
+  int32_t blend_h, blend_w;       /* blend extents (rows / columns) */
+  int32_t limit_h, limit_w;       /* crop of every tile */
+  void* out;
+} vgpa_compose_args;
+int vgpa_vae_compose_tiles_bf16(const vgpa_compose_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

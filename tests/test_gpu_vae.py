@@ -1,0 +1,196 @@
+"""GPU parity of the VAE decoder kernels against the torch oracle (oracle/vae_torch.py,
+parity unpinned against diffusers — see its header) on seeded random weights. Tolerances are stated per test:
+single ops compare against fp32 torch on bf16-rounded inputs (<= 1e-2 of the max), the whole decoder (about 40
+bf16 layers deep) against the fp32 oracle on bf16-rounded weights (<= 6e-2 of the max, mean error <= 1e-2)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vae_torch as V
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def relmax(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12)).item()
+
+
+def small_cfg():
+    return V.VAEConfig(block_out_channels=(64, 64, 64, 128), sample_height=96, sample_width=160)
+
+
+def make_decoder(cfg, sd):
+    from videogpa_b200.vae import AutoencoderKLCogVideoXDecoder, VAEDecoderConfig
+    dcfg = VAEDecoderConfig(block_out_channels=cfg.block_out_channels, sample_height=cfg.sample_height, sample_width=cfg.sample_width)
+    return AutoencoderKLCogVideoXDecoder(sd, dcfg, device="cuda")
+
+
+@pytest.mark.parametrize("T,H,W,Cin,Cout,KT", [(2, 12, 20, 64, 64, 3), (3, 30, 45, 128, 256, 3), (1, 9, 17, 64, 128, 3),
+                                                (4, 16, 16, 64, 64, 1), (2, 24, 40, 128, 3, 3), (2, 11, 13, 256, 512, 3)])
+def test_conv3d_vs_torch(lib, T, H, W, Cin, Cout, KT):
+    from videogpa_b200 import _lib
+    from videogpa_b200.vae import _pad_cout
+    g = torch.Generator().manual_seed(T * 100 + H)
+    x = torch.randn(T + KT - 1, H, W, Cin, generator=g).to(BF)                      # already time-padded
+    w = (torch.randn(Cout, Cin, KT, 3, 3, generator=g) * (1.0 / (Cin * 9 * KT)) ** 0.5).to(BF)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(BF)
+    res = torch.randn(T, H, W, Cout, generator=g).to(BF) if Cout >= 16 else None
+    cp = _pad_cout(Cout)
+    w2 = torch.zeros(cp, KT, 3, 3, Cin, dtype=BF)
+    w2[:Cout] = w.permute(0, 2, 3, 4, 1)
+    b2 = torch.zeros(cp, dtype=BF); b2[:Cout] = b
+    ldo = 16 if cp == 16 else Cout
+    out = torch.zeros(T, H, W, ldo, dtype=BF, device="cuda")
+    xc, wc, bc = x.cuda(), w2.reshape(cp, -1).contiguous().cuda(), b2.cuda()
+    rc = res.cuda() if res is not None else None
+    a = _lib.Conv3dArgs()
+    a.x, a.w, a.bias, a.out = xc.data_ptr(), wc.data_ptr(), bc.data_ptr(), out.data_ptr()
+    a.residual = rc.data_ptr() if rc is not None else None
+    a.T, a.H, a.W, a.Cin, a.Cout, a.Cout_pad, a.KT, a.ldo, a.ld_res = T, H, W, Cin, Cout, cp, KT, ldo, Cout
+    _lib.check(lib.vgpa_conv3d_causal_bf16(C.byref(a), None), "conv")
+    torch.cuda.synchronize()
+    ref = F.conv3d(x.float().permute(3, 0, 1, 2)[None], w.float(), b.float(), padding=(0, 1, 1))[0].permute(1, 2, 3, 0)
+    if res is not None:
+        ref = ref.to(BF).float() + res.float()
+    got = out.cpu().float()[..., :Cout]
+    assert relmax(got, ref) < 1e-2
+    if cp == 16:
+        assert (out.cpu()[..., Cout:] == 0).all()
+
+
+def test_groupnorm_spatialnorm_vs_torch(lib):
+    from videogpa_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    T, H, W, Cc, G = 5, 12, 20, 128, 32
+    Tz, Hz, Wz = 3, 6, 10
+    x = (torch.randn(T, H, W, Cc, generator=g) * 2 + 0.5).to(BF)
+    gamma, beta = (1 + 0.1 * torch.randn(Cc, generator=g)).to(BF), (0.1 * torch.randn(Cc, generator=g)).to(BF)
+    yb = torch.randn(Tz * Hz * Wz, 2 * Cc + 64, generator=g).to(BF)               # padded row stride on purpose
+    xc = x.cuda()
+    ws = torch.empty(lib.vgpa_groupnorm_workspace_bytes(Cc), dtype=torch.uint8, device="cuda")
+    st = torch.empty(2 * G, dtype=torch.float32, device="cuda")
+    _lib.check(lib.vgpa_groupnorm_stats_bf16(xc.data_ptr(), T * H * W, Cc, G, 1e-6, ws.data_ptr(), ws.numel(), st.data_ptr(), None), "gn")
+    xf = x.float().reshape(-1, G, Cc // G)
+    mean = xf.mean(dim=(0, 2)); var = xf.var(dim=(0, 2), unbiased=False)
+    np.testing.assert_allclose(st[:G].cpu().numpy(), mean.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(st[G:].cpu().numpy(), (var + 1e-6).rsqrt().numpy(), rtol=1e-4)
+    from videogpa_b200.vae import AutoencoderKLCogVideoXDecoder as D
+    tz = D._tz_map(T, Tz)
+    assert tz == [0, 1, 1, 2, 2]
+    assert D._tz_map(8, 2) == [0, 0, 0, 0, 1, 1, 1, 1] and D._tz_map(9, 3) == [0, 1, 1, 1, 1, 2, 2, 2, 2] and D._tz_map(1, 1) == [0]
+    out = torch.empty(T, H, W, Cc, dtype=BF, device="cuda")
+    ybc = yb.cuda()
+    a = _lib.SpatialNormArgs()
+    a.x, a.out, a.mean_rstd, a.gamma, a.beta = xc.data_ptr(), out.data_ptr(), st.data_ptr(), gamma.cuda().data_ptr(), beta.cuda().data_ptr()
+    gm, bt = gamma.cuda(), beta.cuda()
+    a.gamma, a.beta = gm.data_ptr(), bt.data_ptr()
+    a.y_lat, a.b_lat, a.ld_lat = ybc.data_ptr(), ybc.data_ptr() + Cc * 2, ybc.stride(0)
+    a.T, a.H, a.W, a.C, a.groups, a.Hz, a.Wz, a.shift, a.silu = T, H, W, Cc, G, Hz, Wz, 1, 1
+    for i, v in enumerate(tz):
+        a.tz_of_t[i] = v
+    _lib.check(lib.vgpa_spatialnorm_apply_bf16(C.byref(a), None), "sn")
+    torch.cuda.synchronize()
+    # torch restatement in the reference's layout: nearest resize of zq (first frame separate), GroupNorm, * y + b, SiLU
+    f = x.float().permute(3, 0, 1, 2)[None]
+    ylat = yb[:, :Cc].float().reshape(Tz, Hz, Wz, Cc).permute(3, 0, 1, 2)[None]
+    blat = yb[:, Cc:2 * Cc].float().reshape(Tz, Hz, Wz, Cc).permute(3, 0, 1, 2)[None]
+    up = lambda z: torch.cat([F.interpolate(z[:, :, :1], size=(1, H, W)), F.interpolate(z[:, :, 1:], size=(T - 1, H, W))], dim=2)
+    ref = F.silu(F.group_norm(f, G, gamma.float(), beta.float(), eps=1e-6) * up(ylat) + up(blat))[0].permute(1, 2, 3, 0)
+    assert relmax(out.cpu(), ref) < 1e-2
+
+
+def test_upsample_and_compose_vs_oracle(lib):
+    from videogpa_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 5, 7, 64, generator=g).to(BF)
+    t_src = [0, 1, 1, 2, 2]
+    out = torch.empty(5, 10, 14, 64, dtype=BF, device="cuda")
+    arr = (C.c_int32 * 16)(*(t_src + [0] * 11))
+    xc = x.cuda()
+    _lib.check(lib.vgpa_upsample_nearest_bf16(xc.data_ptr(), out.data_ptr(), 5, 5, 7, 64, arr, None), "up")
+    xcf = x.permute(3, 0, 1, 2)[None].float()
+    ref = torch.cat([F.interpolate(xcf[:, :, 0], scale_factor=2.0)[:, :, None], F.interpolate(xcf[:, :, 1:], scale_factor=2.0)], dim=2)
+    assert torch.equal(out.cpu().float(), ref[0].permute(1, 2, 3, 0))
+    # compose: 3x3 tiles with the reference geometry scaled down (tile 48x80, blend 8/16, limit 40/64) against the oracle's
+    # in-place blend_v / blend_h on bf16 tensors
+    T, th, tw = 2, [48, 48, 16], [80, 80, 32]
+    tiles = [[torch.randn(1, 3, T, th[i], tw[j], generator=g).to(BF) for j in range(3)] for i in range(3)]
+    a = _lib.ComposeArgs()
+    keep = []
+    for i in range(3):
+        for j in range(3):
+            cl = torch.zeros(T, th[i], tw[j], 16, dtype=BF)
+            cl[..., :3] = tiles[i][j][0].permute(1, 2, 3, 0)
+            keep.append(cl.cuda())
+            a.tiles[i * 3 + j] = keep[-1].data_ptr()
+    H, W = 40 + 40 + 16, 64 + 64 + 32
+    res = torch.empty(3, T, H, W, dtype=BF, device="cuda")
+    a.rows, a.cols = 3, 3
+    for i in range(3):
+        a.th[i], a.tw[i] = th[i], tw[i]
+    a.T, a.H, a.W, a.ldc, a.blend_h, a.blend_w, a.limit_h, a.limit_w, a.out = T, H, W, 16, 8, 16, 40, 64, res.data_ptr()
+    _lib.check(lib.vgpa_vae_compose_tiles_bf16(C.byref(a), None), "compose")
+    rows = [[t.clone() for t in r] for r in tiles]
+    result_rows = []
+    for i, row in enumerate(rows):
+        rr = []
+        for j, tile in enumerate(row):
+            if i > 0:
+                tile = V.blend_v(rows[i - 1][j], tile, 8)
+            if j > 0:
+                tile = V.blend_h(row[j - 1], tile, 16)
+            rr.append(tile[:, :, :, :40, :64])
+        result_rows.append(torch.cat(rr, dim=4))
+    ref = torch.cat(result_rows, dim=3)[0]
+    got = res.cpu()
+    assert got.shape == ref.shape
+    mism = (got != ref).float().mean().item()
+    assert mism < 2e-3 and relmax(got, ref) < 1e-2, mism
+
+
+def _bf16_sd(sd):
+    return {k: v.to(BF).float() for k, v in sd.items()}
+
+
+def test_decoder_untiled_vs_oracle(lib):
+    cfg = small_cfg()
+    sd = _bf16_sd(V.random_state_dict(cfg, seed=11))
+    dec = make_decoder(cfg, sd)
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(1, 16, 5, 6, 10, generator=g).to(BF)                           # one latent tile, 3 frame batches
+    out = dec.decode(z.cuda()).sample.cpu().float()
+    ref = V.decode(sd, cfg, z.float(), tiling=False)
+    assert out.shape == ref.shape == (1, 3, 17, 48, 80)
+    err = (out - ref).abs()
+    assert relmax(out, ref) < 6e-2 and err.mean().item() < 1e-2 * ref.abs().max().item(), (relmax(out, ref), err.mean().item())
+
+
+def test_decoder_tiled_vs_oracle(lib):
+    cfg = small_cfg()
+    sd = _bf16_sd(V.random_state_dict(cfg, seed=12))
+    dec = make_decoder(cfg, sd)
+    dec.enable_tiling(); dec.enable_slicing()
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(1, 16, 3, 12, 20, generator=g).to(BF)                          # 3x3 latent tiles of 6x10, stride 5x8
+    out = dec.decode(z.cuda()).sample.cpu().float()
+    ref = V.decode(sd, cfg, z.float(), tiling=True)
+    assert out.shape == ref.shape == (1, 3, 9, 96, 160)
+    err = (out - ref).abs()
+    assert relmax(out, ref) < 6e-2 and err.mean().item() < 1e-2 * ref.abs().max().item(), (relmax(out, ref), err.mean().item())
+    # tiling changes the result (GroupNorm statistics are per tile): the untiled decode must differ measurably
+    dec.disable_tiling()
+    out2 = dec.decode(z.cuda()).sample.cpu().float()
+    assert (out2 - out).abs().max().item() > 10 * err.mean().item()
+
+
+def test_decoder_rejects_cpu_and_bad_shapes(lib):
+    cfg = small_cfg()
+    dec = make_decoder(cfg, V.random_state_dict(cfg, seed=13))
+    with pytest.raises(RuntimeError):
+        dec.decode(torch.zeros(1, 16, 1, 6, 10))
+    with pytest.raises(RuntimeError):
+        dec.decode(torch.zeros(1, 8, 1, 6, 10, device="cuda"))

@@ -78,6 +78,36 @@ class SchedArgs(C.Structure):
     ]
 
 
+class Conv3dArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("residual", c_void_p), ("out", c_void_p),
+        ("T", c_i32), ("H", c_i32), ("W", c_i32), ("Cin", c_i32), ("Cout", c_i32), ("Cout_pad", c_i32), ("KT", c_i32),
+        ("ldo", c_i32), ("ld_res", c_i32),
+    ]
+
+
+class SpatialNormArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("out", c_void_p), ("mean_rstd", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+        ("y_lat", c_void_p), ("b_lat", c_void_p), ("ld_lat", c_i64),
+        ("T", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32), ("groups", c_i32),
+        ("Hz", c_i32), ("Wz", c_i32), ("shift", c_i32),
+        ("tz_of_t", c_i32 * 16),
+        ("silu", c_i32),
+    ]
+
+
+class ComposeArgs(C.Structure):
+    _fields_ = [
+        ("tiles", c_void_p * 16),
+        ("rows", c_i32), ("cols", c_i32),
+        ("th", c_i32 * 4), ("tw", c_i32 * 4),
+        ("T", c_i32), ("H", c_i32), ("W", c_i32), ("ldc", c_i32),
+        ("blend_h", c_i32), ("blend_w", c_i32), ("limit_h", c_i32), ("limit_w", c_i32),
+        ("out", c_void_p),
+    ]
+
+
 EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV, EPI_ACCUM = 0, 1, 2, 3, 4
 ACT_NONE, ACT_SILU = 0, 1
 SCHED_DDIM, SCHED_DPM = 0, 1
@@ -115,6 +145,12 @@ SIGNATURES = {
     "vgpa_dpo_workspace_bytes": (C.c_size_t, [c_int, c_i64]),
     "vgpa_dpo_loss_forward": (c_int, [C.POINTER(DpoArgs), c_void_p]),
     "vgpa_dpo_loss_backward": (c_int, [C.POINTER(DpoArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vgpa_conv3d_causal_bf16": (c_int, [C.POINTER(Conv3dArgs), c_void_p]),
+    "vgpa_groupnorm_workspace_bytes": (C.c_size_t, [c_int]),
+    "vgpa_groupnorm_stats_bf16": (c_int, [c_void_p, c_i64, c_int, c_int, c_float, c_void_p, C.c_size_t, c_void_p, c_void_p]),
+    "vgpa_spatialnorm_apply_bf16": (c_int, [C.POINTER(SpatialNormArgs), c_void_p]),
+    "vgpa_upsample_nearest_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, C.POINTER(c_i32), c_void_p]),
+    "vgpa_vae_compose_tiles_bf16": (c_int, [C.POINTER(ComposeArgs), c_void_p]),
 }
 
 

@@ -1,0 +1,422 @@
+"""CogVideoX 3-D causal-conv VAE decoder on the sm_100a kernels — drop-in for the part of diffusers'
+AutoencoderKLCogVideoX the reference uses: `vae.enable_tiling()`, `vae.enable_slicing()`, `vae.decode(z).sample`,
+`vae.config.scaling_factor`, `vae.dtype` (generate/CogVideoX-5B.py:20-21,72-77).
+
+Every arithmetic step is a C-ABI kernel (include/videogpa_b200.h): the 3x3x3 / 1x3x3 convolutions are implicit GEMMs
+on tcgen05 (vgpa_conv3d_causal_bf16), the 1x1x1 shortcuts and the conv_y / conv_b projections of SpatialNorm3D are
+the DiT GEMM (vgpa_linear_bf16), GroupNorm statistics + SpatialNorm apply + SiLU, the nearest upsample and the tile
+blend are HBM-bound kernels. torch is used for device memory, views and frame copies (conv_cache) only.
+
+Layout: activations are channels-last [T, H, W, C] bf16 per latent tile and frame batch. The reference semantics
+that change results are kept: frame batching (2 latent frames per decoder pass, the first pass takes the remainder),
+conv_cache carry-over between passes, GroupNorm statistics per (tile, frame batch), 3x3 latent tiles of 30x45 with
+stride 25x36 blended over 40 / 72 px and cropped to 200x288 px.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib, dense
+from ._lib import ComposeArgs, Conv3dArgs, SpatialNormArgs
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class VAEDecoderConfig:
+    latent_channels: int = 16
+    out_channels: int = 3
+    block_out_channels: tuple = (128, 256, 256, 512)
+    layers_per_block: int = 3
+    norm_num_groups: int = 32
+    temporal_compression_ratio: int = 4
+    scaling_factor: float = 0.7
+    sample_height: int = 480
+    sample_width: int = 720
+    num_latent_frames_batch_size: int = 2
+    tile_overlap_factor_height: float = 1 / 6
+    tile_overlap_factor_width: float = 1 / 5
+
+
+class DecoderOutput(SimpleNamespace):
+    """`.sample` like diffusers' DecoderOutput."""
+
+
+class _Conv:
+    __slots__ = ("w", "b", "kt", "cin", "cout", "cout_pad")
+
+
+class _SNorm:
+    __slots__ = ("gamma", "beta", "c", "off")      # off: first column of this norm's conv_y block in the fused projection
+
+
+def _pad_cout(c: int) -> int:
+    if c % 256 == 0 or c in (64, 128):
+        return c
+    if c <= 16:
+        return 16
+    raise RuntimeError(f"VAE conv with {c} output channels is not supported (need 64, 128 or a multiple of 256)")
+
+
+class AutoencoderKLCogVideoXDecoder:
+    def __init__(self, state_dict: dict, config: VAEDecoderConfig | None = None, device="cuda"):
+        self.config = config or VAEDecoderConfig()
+        self.device = torch.device(device)
+        self.dtype = BF16
+        self.use_tiling = False
+        self.use_slicing = False
+        c = self.config
+        self.rc = tuple(reversed(c.block_out_channels))
+        self.temporal_compress_level = int(math.log2(c.temporal_compression_ratio))
+        self.zc_pad = 64                                                    # latent channels padded to one K block
+        if c.latent_channels > self.zc_pad:
+            raise RuntimeError("latent_channels > 64 is not supported")
+        self._norm_cols = 0
+        self._yb_w, self._yb_b = [], []
+        self._load(state_dict)
+        self._ws = None
+        # tiling geometry (AutoencoderKLCogVideoX.__init__)
+        self.tile_sample_min_height = c.sample_height // 2
+        self.tile_sample_min_width = c.sample_width // 2
+        scale = 2 ** (len(c.block_out_channels) - 1)
+        self.spatial_scale = scale
+        self.tile_latent_min_height = int(self.tile_sample_min_height / scale)
+        self.tile_latent_min_width = int(self.tile_sample_min_width / scale)
+
+    # ------------------------------------------------------------------ weights
+    def _conv(self, sd, name, pad_cin_to: int | None = None) -> _Conv:
+        if name + ".weight" not in sd:
+            raise RuntimeError(f"state dict is missing {name}.weight")
+        w = sd[name + ".weight"].to(device=self.device, dtype=torch.float32)
+        b = sd[name + ".bias"].to(device=self.device, dtype=torch.float32)
+        if w.dim() == 4:                                                    # Conv2d of the upsampler: [co, ci, 3, 3]
+            w = w[:, :, None]
+        co, ci, kt, kh, kw = w.shape
+        if (kh, kw) != (3, 3) or kt not in (1, 3):
+            raise RuntimeError(f"{name}: unsupported kernel {tuple(w.shape)}")
+        cin = ci if pad_cin_to is None else pad_cin_to
+        if cin % 64 != 0:
+            raise RuntimeError(f"{name}: input channels {cin} must be a multiple of 64")
+        cp = _pad_cout(co)
+        w2 = torch.zeros(cp, kt, kh, kw, cin, device=self.device, dtype=torch.float32)
+        w2[:co, :, :, :, :ci] = w.permute(0, 2, 3, 4, 1)
+        bb = torch.zeros(cp, device=self.device, dtype=torch.float32)
+        bb[:co] = b
+        cv = _Conv()
+        cv.w = w2.reshape(cp, kt * kh * kw * cin).to(BF16).contiguous()
+        cv.b = bb.to(BF16).contiguous()
+        cv.kt, cv.cin, cv.cout, cv.cout_pad = kt, cin, co, cp
+        return cv
+
+    def _snorm(self, sd, name, ch: int) -> _SNorm:
+        n = _SNorm()
+        n.gamma = sd[name + ".norm_layer.weight"].to(device=self.device, dtype=BF16).contiguous()
+        n.beta = sd[name + ".norm_layer.bias"].to(device=self.device, dtype=BF16).contiguous()
+        n.c = ch
+        n.off = self._norm_cols
+        zc = self.config.latent_channels
+        for part in ("conv_y", "conv_b"):                                   # [C, zc, 1, 1, 1] pointwise convs of zq
+            w = torch.zeros(ch, self.zc_pad, device=self.device, dtype=torch.float32)
+            w[:, :zc] = sd[f"{name}.{part}.conv.weight"].to(device=self.device, dtype=torch.float32).reshape(ch, zc)
+            self._yb_w.append(w)
+            self._yb_b.append(sd[f"{name}.{part}.conv.bias"].to(device=self.device, dtype=torch.float32))
+        self._norm_cols += 2 * ch
+        return n
+
+    def _resnet(self, sd, name, ci, co):
+        r = SimpleNamespace()
+        r.norm1 = self._snorm(sd, name + ".norm1", ci)
+        r.conv1 = self._conv(sd, name + ".conv1.conv")
+        r.norm2 = self._snorm(sd, name + ".norm2", co)
+        r.conv2 = self._conv(sd, name + ".conv2.conv")
+        r.sc_w = r.sc_b = None
+        if ci != co:
+            w = sd[name + ".conv_shortcut.weight"]
+            if w.shape[2:] != (1, 1, 1):
+                raise RuntimeError(f"{name}.conv_shortcut: only the 1x1x1 shortcut of the released checkpoints is supported")
+            r.sc_w = w.reshape(co, ci).to(device=self.device, dtype=BF16).contiguous()
+            r.sc_b = sd[name + ".conv_shortcut.bias"].to(device=self.device, dtype=BF16).contiguous()
+        r.ci, r.co = ci, co
+        return r
+
+    def _load(self, sd: dict) -> None:
+        c, rc = self.config, self.rc
+        self.conv_in = self._conv(sd, "decoder.conv_in.conv", pad_cin_to=self.zc_pad)
+        self.mid = [self._resnet(sd, f"decoder.mid_block.resnets.{j}", rc[0], rc[0]) for j in range(2)]
+        self.up = []
+        cin = rc[0]
+        for i, co in enumerate(rc):
+            blk = SimpleNamespace()
+            blk.resnets = [self._resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", cin if j == 0 else co, co)
+                           for j in range(c.layers_per_block + 1)]
+            blk.upsample = None
+            if i != len(rc) - 1:
+                blk.upsample = self._conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv")
+                blk.compress_time = i < self.temporal_compress_level
+            self.up.append(blk)
+            cin = co
+        self.norm_out = self._snorm(sd, "decoder.norm_out", rc[-1])
+        self.conv_out = self._conv(sd, "decoder.conv_out.conv")
+        # one fused projection for every conv_y / conv_b of the decoder: [sum 2C, 64]
+        ncol = self._norm_cols
+        ncol_pad = (ncol + 255) // 256 * 256
+        W = torch.zeros(ncol_pad, self.zc_pad, device=self.device, dtype=torch.float32)
+        B = torch.zeros(ncol_pad, device=self.device, dtype=torch.float32)
+        W[:ncol] = torch.cat(self._yb_w, 0)
+        B[:ncol] = torch.cat(self._yb_b, 0)
+        self.yb_w, self.yb_b = W.to(BF16).contiguous(), B.to(BF16).contiguous()
+        self._yb_w = self._yb_b = None
+
+    # ------------------------------------------------------------------ diffusers-style switches
+    def enable_tiling(self, *a, **k):
+        self.use_tiling = True
+
+    def disable_tiling(self):
+        self.use_tiling = False
+
+    def enable_slicing(self):
+        self.use_slicing = True
+
+    def disable_slicing(self):
+        self.use_slicing = False
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    # ------------------------------------------------------------------ kernel wrappers
+    def _gn_stats(self, x: torch.Tensor, C_: int) -> torch.Tensor:
+        lib = _lib.load()
+        need = lib.vgpa_groupnorm_workspace_bytes(C_)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=self.device)
+        out = torch.empty(2 * self.config.norm_num_groups, dtype=torch.float32, device=self.device)
+        n_pix = x.numel() // C_
+        _lib.check(lib.vgpa_groupnorm_stats_bf16(x.data_ptr(), n_pix, C_, self.config.norm_num_groups, 1e-6, self._ws.data_ptr(),
+                                                 self._ws.numel(), out.data_ptr(), _lib.current_stream()), "vgpa_groupnorm_stats_bf16")
+        return out
+
+    @staticmethod
+    def _tz_map(T: int, Tz: int):
+        """Frame of zq seen by frame t of a [T]-frame feature map (CogVideoXSpatialNorm3D's nearest resize)."""
+        if T > 1 and T % 2 == 1:
+            rest = [1 + int(math.floor((k) * ((Tz - 1) / (T - 1)))) for k in range(T - 1)] if Tz > 1 else [0] * (T - 1)
+            return [0] + rest
+        return [int(math.floor(k * (Tz / T))) for k in range(T)]
+
+    def _snorm_apply(self, x, norm: _SNorm, yb, zshape, out, silu: bool):
+        """x [T,H,W,C] -> out (same shape, may be a view 2 frames into a time-padded buffer)."""
+        lib = _lib.load()
+        T, H, W, C_ = x.shape
+        Tz, Hz, Wz = zshape
+        stats = self._gn_stats(x, C_)
+        a = SpatialNormArgs()
+        a.x, a.out, a.mean_rstd = x.data_ptr(), out.data_ptr(), stats.data_ptr()
+        a.gamma, a.beta = norm.gamma.data_ptr(), norm.beta.data_ptr()
+        esz = yb.element_size()
+        a.y_lat = yb.data_ptr() + norm.off * esz
+        a.b_lat = yb.data_ptr() + (norm.off + C_) * esz
+        a.ld_lat = yb.stride(0)
+        a.T, a.H, a.W, a.C, a.groups = T, H, W, C_, self.config.norm_num_groups
+        a.Hz, a.Wz = Hz, Wz
+        shift = int(round(math.log2(H / Hz))) if H >= Hz else 0
+        if (Hz << shift) < H or (Wz << shift) < W:
+            raise RuntimeError(f"feature map {H}x{W} is not a power-of-two multiple of the latent tile {Hz}x{Wz}")
+        a.shift = shift
+        for i, tz in enumerate(self._tz_map(T, Tz)):
+            a.tz_of_t[i] = tz
+        a.silu = 1 if silu else 0
+        _lib.check(lib.vgpa_spatialnorm_apply_bf16(C.byref(a), _lib.current_stream()), "vgpa_spatialnorm_apply_bf16")
+
+    def _conv_call(self, cv: _Conv, xpad: torch.Tensor, T: int, out: torch.Tensor | None = None, residual=None) -> torch.Tensor:
+        lib = _lib.load()
+        Tp, H, W, Cin = xpad.shape
+        if Tp != T + cv.kt - 1 or Cin != cv.cin:
+            raise RuntimeError(f"conv input {tuple(xpad.shape)} does not match T={T}, kt={cv.kt}, Cin={cv.cin}")
+        ldo = 16 if cv.cout_pad == 16 else cv.cout
+        if out is None:
+            out = torch.empty((T, H, W, ldo), dtype=BF16, device=self.device)
+        a = Conv3dArgs()
+        a.x, a.w, a.bias, a.out = xpad.data_ptr(), cv.w.data_ptr(), cv.b.data_ptr(), out.data_ptr()
+        a.residual = residual.data_ptr() if residual is not None else None
+        a.T, a.H, a.W, a.Cin, a.Cout, a.Cout_pad, a.KT = T, H, W, Cin, cv.cout, cv.cout_pad, cv.kt
+        a.ldo = ldo
+        a.ld_res = residual.shape[-1] if residual is not None else 0
+        _lib.check(lib.vgpa_conv3d_causal_bf16(C.byref(a), _lib.current_stream()), "vgpa_conv3d_causal_bf16")
+        return out
+
+    def _finish_timepad(self, buf: torch.Tensor, key: str, cache_in: dict | None, cache_out: dict):
+        """buf [T+2, H, W, C] with frames [2:] already written: fill the 2 leading frames from the conv_cache (or
+        replicate the first frame) and record the new cache = last 2 frames of the padded input."""
+        if cache_in is not None and key in cache_in:
+            buf[:2].copy_(cache_in[key])
+        else:
+            buf[0].copy_(buf[2])
+            buf[1].copy_(buf[2])
+        cache_out[key] = buf[-2:].clone()
+
+    def _norm_conv(self, x, norm, cv, key, yb, zshape, cache_in, cache_out, residual=None, out=None):
+        """SpatialNorm -> SiLU -> causal conv (the repeated unit of CogVideoXResnetBlock3D and the output head)."""
+        T, H, W, C_ = x.shape
+        buf = torch.empty((T + 2, H, W, C_), dtype=BF16, device=self.device)
+        self._snorm_apply(x, norm, yb, zshape, buf[2:], silu=True)
+        self._finish_timepad(buf, key, cache_in, cache_out)
+        return self._conv_call(cv, buf, T, out=out, residual=residual)
+
+    def _resnet_fwd(self, r, x, key, yb, zshape, cache_in, cache_out):
+        T, H, W, _ = x.shape
+        h = self._norm_conv(x, r.norm1, r.conv1, key + ".conv1", yb, zshape, cache_in, cache_out)
+        res = x
+        if r.sc_w is not None:
+            res = dense.linear(x.view(-1, r.ci), r.sc_w, r.sc_b).view(T, H, W, r.co)
+        return self._norm_conv(h, r.norm2, r.conv2, key + ".conv2", yb, zshape, cache_in, cache_out, residual=res)
+
+    def _upsample_fwd(self, blk, x):
+        lib = _lib.load()
+        T, H, W, C_ = x.shape
+        if blk.compress_time and T > 1:
+            t_src = [0] + [1 + k // 2 for k in range(2 * (T - 1))] if T % 2 == 1 else [k // 2 for k in range(2 * T)]
+        else:
+            t_src = list(range(T))
+        To = len(t_src)
+        if To > 16:
+            raise RuntimeError("more than 16 frames per decoder pass are not supported")
+        up = torch.empty((To, 2 * H, 2 * W, C_), dtype=BF16, device=self.device)
+        arr = (C.c_int32 * 16)(*(t_src + [0] * (16 - To)))
+        _lib.check(lib.vgpa_upsample_nearest_bf16(x.data_ptr(), up.data_ptr(), To, H, W, C_, arr, _lib.current_stream()),
+                   "vgpa_upsample_nearest_bf16")
+        return self._conv_call(blk.upsample, up, To)
+
+    # ------------------------------------------------------------------ one decoder pass over one frame batch of one tile
+    def _decoder_pass(self, zt: torch.Tensor, cache_in: dict | None, out: torch.Tensor):
+        """zt [Tz, hz, wz, 64] channels-last padded latent; out [T_out, 8hz, 8wz, 16] receives the frames."""
+        Tz, hz, wz, _ = zt.shape
+        zshape = (Tz, hz, wz)
+        cache_out: dict = {}
+        yb = dense.linear(zt.view(-1, self.zc_pad), self.yb_w, self.yb_b)          # conv_y / conv_b of every SpatialNorm
+        buf = torch.empty((Tz + 2, hz, wz, self.zc_pad), dtype=BF16, device=self.device)
+        buf[2:].copy_(zt)
+        self._finish_timepad(buf, "conv_in", cache_in, cache_out)
+        h = self._conv_call(self.conv_in, buf, Tz)
+        for j, r in enumerate(self.mid):
+            h = self._resnet_fwd(r, h, f"mid.{j}", yb, zshape, cache_in, cache_out)
+        for i, blk in enumerate(self.up):
+            for j, r in enumerate(blk.resnets):
+                h = self._resnet_fwd(r, h, f"up.{i}.{j}", yb, zshape, cache_in, cache_out)
+            if blk.upsample is not None:
+                h = self._upsample_fwd(blk, h)
+        if tuple(out.shape[:3]) != tuple(h.shape[:3]):
+            raise RuntimeError(f"decoder pass produced {tuple(h.shape)}, expected {tuple(out.shape)}")
+        self._norm_conv(h, self.norm_out, self.conv_out, "conv_out", yb, zshape, cache_in, cache_out, out=out)
+        return cache_out
+
+    @staticmethod
+    def frame_batches(num_frames: int, fb: int):
+        nb = max(num_frames // fb, 1)
+        rem = num_frames % fb
+        return [(fb * i + (0 if i == 0 else rem), fb * (i + 1) + rem) for i in range(nb)]
+
+    def _frames_out(self, n_latent: int, first: bool) -> int:
+        """Output frames of a decoder pass over n_latent latent frames (first pass keeps the leading frame single)."""
+        T = n_latent
+        for _ in range(self.temporal_compress_level):
+            T = (1 + 2 * (T - 1)) if (T > 1 and T % 2 == 1) else (2 * T if T > 1 else 1)
+        return T
+
+    def _decode_tile(self, zt: torch.Tensor) -> torch.Tensor:
+        """zt [T, hz, wz, 64] -> [T_out, 8hz, 8wz, 16] (first 3 channels = RGB)."""
+        T, hz, wz, _ = zt.shape
+        batches = self.frame_batches(T, self.config.num_latent_frames_batch_size)
+        touts = [self._frames_out(e - s, i == 0) for i, (s, e) in enumerate(batches)]
+        s8 = self.spatial_scale
+        out = torch.empty((sum(touts), hz * s8, wz * s8, 16), dtype=BF16, device=self.device)
+        cache = None
+        t0 = 0
+        for (s, e), to in zip(batches, touts):
+            cache = self._decoder_pass(zt[s:e].contiguous(), cache, out[t0:t0 + to])
+            t0 += to
+        return out
+
+    # ------------------------------------------------------------------ public decode
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, return_dict: bool = True):
+        """z [B, C, T, h, w] (already divided by scaling_factor) -> .sample [B, 3, T_out, 8h, 8w] bf16."""
+        lib = _lib.load()
+        if not isinstance(z, torch.Tensor) or not z.is_cuda:
+            raise RuntimeError("decode needs a CUDA tensor (no CPU fallback exists)")
+        if z.dim() != 5 or z.shape[1] != self.config.latent_channels:
+            raise RuntimeError(f"z must be [B, {self.config.latent_channels}, T, h, w]")
+        B, Cz, T, H, W = z.shape
+        c = self.config
+        zcl = torch.zeros((B, T, H, W, self.zc_pad), dtype=BF16, device=self.device)
+        zcl[..., :Cz] = z.to(BF16).permute(0, 2, 3, 4, 1)
+        tlh, tlw = self.tile_latent_min_height, self.tile_latent_min_width
+        tiled = self.use_tiling and (W > tlw or H > tlh)
+        if tiled:
+            oh, ow = int(tlh * (1 - c.tile_overlap_factor_height)), int(tlw * (1 - c.tile_overlap_factor_width))
+            bh = int(self.tile_sample_min_height * c.tile_overlap_factor_height)
+            bw = int(self.tile_sample_min_width * c.tile_overlap_factor_width)
+            lh, lw = self.tile_sample_min_height - bh, self.tile_sample_min_width - bw
+            ys, xs = list(range(0, H, oh)), list(range(0, W, ow))
+        else:
+            oh = ow = bh = bw = 0
+            lh, lw = H * self.spatial_scale, W * self.spatial_scale
+            ys, xs = [0], [0]
+            tlh, tlw = H, W
+        if len(ys) > 4 or len(xs) > 4:
+            raise RuntimeError("tiled decode supports at most 4x4 tiles")
+        s8 = self.spatial_scale
+        samples = []
+        for b in range(B):
+            tiles = []
+            for y0 in ys:
+                for x0 in xs:
+                    tiles.append(self._decode_tile(zcl[b, :, y0:y0 + tlh, x0:x0 + tlw].contiguous()))
+            To = tiles[0].shape[0]
+            out = torch.empty((3, To, H * s8, W * s8), dtype=BF16, device=self.device)
+            a = ComposeArgs()
+            for k, t in enumerate(tiles):
+                a.tiles[k] = t.data_ptr()
+            a.rows, a.cols = len(ys), len(xs)
+            for i in range(len(ys)):
+                a.th[i] = tiles[i * len(xs)].shape[1]
+            for j in range(len(xs)):
+                a.tw[j] = tiles[j].shape[2]
+            a.T, a.H, a.W, a.ldc = To, H * s8, W * s8, 16
+            a.blend_h, a.blend_w, a.limit_h, a.limit_w = bh, bw, lh, lw
+            a.out = out.data_ptr()
+            _lib.check(lib.vgpa_vae_compose_tiles_bf16(C.byref(a), _lib.current_stream()), "vgpa_vae_compose_tiles_bf16")
+            samples.append(out)
+        sample = torch.stack(samples, 0)
+        if not return_dict:
+            return (sample,)
+        return DecoderOutput(sample=sample)
+
+    # ------------------------------------------------------------------ bookkeeping for bench.py
+    def conv_flops(self, T_lat: int, H: int, W: int) -> float:
+        """Algorithmic conv FLOPs of an UNTILED decode of [T_lat, H, W] latents (2 * pixels * K * Cout per conv)."""
+        rc = self.rc
+        fl = 0.0
+        Tcur, h, w = T_lat, H, W
+        fl += 2.0 * Tcur * h * w * 27 * self.config.latent_channels * rc[0]
+        res = lambda ci, co, px: 2.0 * px * 27 * (ci * co + co * co) + (2.0 * px * ci * co if ci != co else 0.0)
+        fl += 2 * res(rc[0], rc[0], Tcur * h * w)
+        cin = rc[0]
+        for i, co in enumerate(rc):
+            px = Tcur * h * w
+            fl += res(cin, co, px) + self.config.layers_per_block * res(co, co, px)
+            if i != len(rc) - 1:
+                if i < self.temporal_compress_level:
+                    Tcur = 1 + 2 * (Tcur - 1) if Tcur > 1 else 1
+                h, w = 2 * h, 2 * w
+                fl += 2.0 * Tcur * h * w * 9 * co * co
+            cin = co
+        fl += 2.0 * Tcur * h * w * 27 * rc[-1] * self.config.out_channels
+        return fl
