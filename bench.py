@@ -276,6 +276,28 @@ def run_ours(args, rank, world, local):
     except Exception as ex:     # the secondary metric never hides the primary line
         mvcs = {"error": str(ex)}
 
+    # ---- VAE decode of the finished clip (part of the same path; reported separately)
+    vae = None
+    try:
+        from videogpa_b200.vae import AutoencoderKLCogVideoXDecoder, VAEDecoderConfig
+        from oracle.vae_torch import VAEConfig, random_state_dict as vae_random_sd     # weight generator only (no oracle math)
+        dec = AutoencoderKLCogVideoXDecoder(vae_random_sd(VAEConfig(), seed=5, dtype=torch.bfloat16), VAEDecoderConfig(), device=dev)
+        dec.enable_tiling(); dec.enable_slicing()
+        zz = (lat.permute(0, 2, 1, 3, 4) / 0.7).contiguous()
+        dec.decode(zz)
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(2):
+            frames = dec.decode(zz).sample
+        v1.record(); torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1) / 2
+        fl = sum(dec.conv_flops(e - s, hh, ww) for hh in (30, 30, 10) for ww in (45, 45, 18) for (s, e) in dec.frame_batches(13, 2))
+        vae = {"metric": "VAE decode 49f 480x720 (tiled 3x3, frame batches of 2)", "ms_per_clip": vms, "conv_tflop": fl / 1e12,
+               "conv_tflops_per_s": fl / (vms / 1000.0) / 1e12, "frames": list(frames.shape), "weights": "random-init, seed 5"}
+        del dec, frames
+    except Exception as ex:
+        vae = {"error": str(ex)}
+
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -296,7 +318,7 @@ def run_ours(args, rank, world, local):
                      "flops_per_launch": attn_flops, "avg_launch_ms": attn_avg_ms, "launches_timed": len(attn_ms),
                      "share_of_step": (sum(attn_ms) / ms_max) if ms_max > 0 else None},
         "step_tflops": step_flops * args.steps / (ms_max / 1000.0) / 1e12,
-        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs,
+        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae,
     }
     print(json.dumps(line), flush=True)
 

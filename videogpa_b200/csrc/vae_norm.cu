@@ -54,21 +54,32 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, long long n_pixels, int C
   for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) partial[static_cast<long long>(blockIdx.x) * 2 * C + i] = sh[i];
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int groups, double count,
-                                   float eps, float* __restrict__ mean_rstd) {
-  const int g = threadIdx.x;
-  if (g >= groups) return;
+// One block per group: thread i folds partial blocks i, i+256, ... in fp64, then a fixed shared-memory tree.
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int groups, double count,
+                   float eps, float* __restrict__ mean_rstd) {
+  __shared__ double ss[256], sq[256];
+  const int g = blockIdx.x;
   const int cpg = C / groups;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    const float* p = partial + static_cast<long long>(b) * 2 * C;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += p[c]; q += p[C + c]; }
+  for (int b = threadIdx.x; b < nblocks; b += 256) {
+    const float* p = partial + static_cast<long long>(b) * 2 * C + g * cpg;
+    for (int c = 0; c < cpg; ++c) { s += p[c]; q += p[C + c]; }
   }
-  const double mean = s / count;
-  double var = q / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mean_rstd[g] = static_cast<float>(mean);
-  mean_rstd[groups + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  ss[threadIdx.x] = s;
+  sq[threadIdx.x] = q;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) { ss[threadIdx.x] += ss[threadIdx.x + off]; sq[threadIdx.x] += sq[threadIdx.x + off]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = ss[0] / count;
+    double var = sq[0] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[g] = static_cast<float>(mean);
+    mean_rstd[groups + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- SpatialNorm apply
@@ -244,7 +255,7 @@ extern "C" int vgpa_groupnorm_stats_bf16(const void* x, int64_t n_pixels, int C,
   gn_partial_kernel<<<static_cast<int>(nb), GN_THREADS, 2 * C * sizeof(float), s>>>(
       static_cast<const __nv_bfloat16*>(x), n_pixels, C, static_cast<float*>(workspace));
   VGPA_LAUNCH_CHECK("gn_partial_kernel");
-  gn_finalize_kernel<<<1, 64, 0, s>>>(static_cast<const float*>(workspace), static_cast<int>(nb), C, groups,
+  gn_finalize_kernel<<<groups, 256, 0, s>>>(static_cast<const float*>(workspace), static_cast<int>(nb), C, groups,
                                       static_cast<double>(n_pixels) * (C / groups), eps, mean_rstd);
   VGPA_LAUNCH_CHECK("gn_finalize_kernel");
   return 0;
