@@ -280,8 +280,7 @@ def run_ours(args, rank, world, local):
     vae = None
     try:
         from videogpa_b200.vae import AutoencoderKLCogVideoXDecoder, VAEDecoderConfig
-        from oracle.vae_torch import VAEConfig, random_state_dict as vae_random_sd     # weight generator only (no oracle math)
-        dec = AutoencoderKLCogVideoXDecoder(vae_random_sd(VAEConfig(), seed=5, dtype=torch.bfloat16), VAEDecoderConfig(), device=dev)
+        dec = AutoencoderKLCogVideoXDecoder.random_init(VAEDecoderConfig(), seed=5, device=dev)
         dec.enable_tiling(); dec.enable_slicing()
         zz = (lat.permute(0, 2, 1, 3, 4) / 0.7).contiguous()
         dec.decode(zz)

@@ -185,3 +185,27 @@ def test_scheduler_step_vs_oracle(lib):
     m1, m2, mn, r = O.dpm_coefficients(ac, 979, 959, 999)
     k = dpm.coefficients(979, 999)
     assert abs(k["c_sample"] - m1) < 1e-12 and abs(k["c_noise"] - mn) < 1e-12 and abs(k["c_x0"] + m2 * (1 + 1 / (2 * r))) < 1e-12
+
+
+def test_generate_cli_synthetic_end_to_end(lib, tmp_path, capsys):
+    """generate CLI contract on the GPU with a 1-block random-init model: mp4 per prompt under <out>/<group>/seed_<seed>.mp4,
+    resume by skipping existing files, missing --lora_path falls back to the base model (generate/CogVideoX-5B.py:24-80)."""
+    import json
+    from videogpa_b200.generate import cogvideox_5b as g
+    pj = tmp_path / "prompts.json"
+    pj.write_text(json.dumps({"scene/one": "a red cube on a table", "two": {"text_prompt": "a blue sphere"}, "empty": ""}))
+    out = tmp_path / "out"
+    argv = ["--prompt_json", str(pj), "--output_dir", str(out), "--synthetic", "1", "--num_inference_steps", "2",
+            "--num_frames", "9", "--height", "96", "--width", "160", "--seed", "7", "--lora_path", str(tmp_path / "missing_lora")]
+    g.main(argv)
+    first = capsys.readouterr().out
+    assert "LoRA path not found" in first and "Failed" not in first
+    v1, v2 = out / "scene_one" / "seed_7.mp4", out / "two" / "seed_7.mp4"
+    assert v1.exists() and v1.stat().st_size > 1000 and v2.exists() and not (out / "empty").exists()
+    import cv2
+    cap = cv2.VideoCapture(str(v1))
+    n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT)); w = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)); h = int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    assert (n, w, h) == (9, 160, 96)
+    g.main(argv)
+    second = capsys.readouterr().out
+    assert second.count("Skip existing") == 2

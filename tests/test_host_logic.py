@@ -167,3 +167,29 @@ def test_frame_and_pair_index_rules_match_oracle():
         assert sample_frame_indices(total, n).tolist() == o.uniform_frame_indices(total, n).tolist()
     assert consecutive_pairs(4) == list(o.consecutive_pairs(4)) == [(0, 1), (1, 2), (2, 3)]
     assert consecutive_pairs(1) == []
+
+
+def test_generate_cli_surface_and_task_parsing(tmp_path):
+    """The generate CLI keeps the reference's flags/defaults (generate/CogVideoX-5B.py:86-99), prompt-JSON forms and
+    output layout (host logic only; no GPU)."""
+    import json
+    from videogpa_b200.generate import cogvideox_5b as g
+    p = g.build_parser()
+    a = p.parse_args(["--prompt_json", "x.json", "--output_dir", "out"])
+    assert (a.base_model, a.lora_path, a.gpu_id, a.seed, a.num_prompts, a.num_inference_steps, a.guidance_scale, a.fps) == \
+        ("THUDM/CogVideoX-5B", None, 0, 42, None, 50, 6.0, 8)
+    import pytest
+    with pytest.raises(SystemExit):
+        p.parse_args(["--output_dir", "out"])                      # --prompt_json is required
+    f = tmp_path / "p.json"
+    f.write_text(json.dumps({"a/b": "a cat", "c": {"text_prompt": "a dog", "image_prompt": "x.png"}, "d": {"prompt": "a fox"}}))
+    tasks = g.load_tasks(str(f), None)
+    assert [t["text_prompt"] for t in tasks] == ["a cat", "a dog", "a fox"]
+    assert g.load_tasks(str(f), 2) == tasks[:2]
+    gid, path = g.video_path_for(tmp_path, tasks[0], 0, 42)
+    assert gid == "a_b" and path == tmp_path / "a_b" / "seed_42.mp4"
+    f.write_text(json.dumps([{"group_id": 7, "text_prompt": "x"}, {"prompt": "y"}]))
+    tasks = g.load_tasks(str(f), None)
+    assert g.video_path_for(tmp_path, tasks[0], 0, 1)[0] == "7" and g.video_path_for(tmp_path, tasks[1], 1, 1)[0] == "1"
+    f.write_text("3")
+    assert g.load_tasks(str(f), None) is None

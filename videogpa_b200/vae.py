@@ -88,6 +88,49 @@ class AutoencoderKLCogVideoXDecoder:
         self.tile_latent_min_height = int(self.tile_sample_min_height / scale)
         self.tile_latent_min_width = int(self.tile_sample_min_width / scale)
 
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def random_init(cls, config: VAEDecoderConfig | None = None, seed: int = 5, device="cuda") -> "AutoencoderKLCogVideoXDecoder":
+        """Synthetic decoder weights with the diffusers parameter names (no checkpoint is reachable):
+        fan-in scaled normal conv weights, GroupNorm gamma ~ 1, conv_y bias ~ 1 so activations stay O(1)."""
+        cfg = config or VAEDecoderConfig()
+        dev = torch.device(device)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        sd, zc = {}, cfg.latent_channels
+
+        def conv(name, co, ci, *k, scale=None):
+            fan = ci * math.prod(k)
+            sd[name + ".weight"] = (torch.randn(co, ci, *k, generator=g, device=dev) * (scale or (1.0 / fan) ** 0.5)).to(BF16)
+            sd[name + ".bias"] = (torch.randn(co, generator=g, device=dev) * 0.02).to(BF16)
+
+        def snorm(name, ch):
+            sd[name + ".norm_layer.weight"] = (1.0 + 0.1 * torch.randn(ch, generator=g, device=dev)).to(BF16)
+            sd[name + ".norm_layer.bias"] = (0.05 * torch.randn(ch, generator=g, device=dev)).to(BF16)
+            conv(name + ".conv_y.conv", ch, zc, 1, 1, 1, scale=0.05)
+            sd[name + ".conv_y.conv.bias"] = (1.0 + 0.05 * torch.randn(ch, generator=g, device=dev)).to(BF16)
+            conv(name + ".conv_b.conv", ch, zc, 1, 1, 1, scale=0.05)
+
+        def resnet(name, ci, co):
+            snorm(name + ".norm1", ci); conv(name + ".conv1.conv", co, ci, 3, 3, 3)
+            snorm(name + ".norm2", co); conv(name + ".conv2.conv", co, co, 3, 3, 3)
+            if ci != co:
+                conv(name + ".conv_shortcut", co, ci, 1, 1, 1)
+
+        rc = tuple(reversed(cfg.block_out_channels))
+        conv("decoder.conv_in.conv", rc[0], zc, 3, 3, 3)
+        for j in range(2):
+            resnet(f"decoder.mid_block.resnets.{j}", rc[0], rc[0])
+        cin = rc[0]
+        for i, co in enumerate(rc):
+            for j in range(cfg.layers_per_block + 1):
+                resnet(f"decoder.up_blocks.{i}.resnets.{j}", cin if j == 0 else co, co)
+            if i != len(rc) - 1:
+                conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", co, co, 3, 3)
+            cin = co
+        snorm("decoder.norm_out", rc[-1])
+        conv("decoder.conv_out.conv", cfg.out_channels, rc[-1], 3, 3, 3)
+        return cls(sd, cfg, device=dev)
+
     # ------------------------------------------------------------------ weights
     def _conv(self, sd, name, pad_cin_to: int | None = None) -> _Conv:
         if name + ".weight" not in sd:
