@@ -80,10 +80,10 @@ int vgpa_linear_bf16(const vgpa_linear_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1 — joint text+video full attention: out = softmax(q k^T * scale) v per (batch, head), bf16 in/out,
- * fp32 softmax, head_dim 64. Replaces F.scaled_dot_product_attention inside diffusers'
+ * fp32 softmax, head_dim 64 (CogVideoX) or 128 (Wan2.2). Replaces F.scaled_dot_product_attention inside diffusers'
  * CogVideoXAttnProcessor2_0.__call__ (reference call sites
  * generate/CogVideoX-5B.py:72-77, train/CogVideoX-5B/03_train.py:134-151). No mask, no dropout,
- * not causal. Heads are packed along the row: head h of row s lives at columns [h*64, h*64+64).
+ * not causal. Heads are packed along the row: head h of row s lives at columns [h*head_dim, (h+1)*head_dim).
  * q/k/v may alias one fused [B*S, 3*H*64] projection buffer (pass three pointers into it).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct vgpa_attention_args {

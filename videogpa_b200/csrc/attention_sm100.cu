@@ -28,6 +28,7 @@
 //     of MUFU (relative error ~1e-4, below the bf16 rounding of P), balancing the two pipes;
 //   * the row max uses 3-input FMNMX3.
 #include "sm100.cuh"
+#include "attn_common.cuh"
 #include "../../include/videogpa_b200.h"
 #include <math.h>
 #include <stdlib.h>
@@ -53,69 +54,7 @@ struct AttnParams {
   float scale_log2;
 };
 
-// ------------------------------------------------------------------ packed fp32x2 helpers (FFMA2 / FADD2)
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_add_rm(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-// 2^x for a packed pair on the FMA pipe: floor via round-to-minus-inf magic add, degree-3 minimax
-// polynomial of 2^f on [0,1), exponent spliced in with integer shift+add. x <= 127 is guaranteed by
-// the caller (x <= AT_RESCALE_THRESHOLD); x is clamped at -127 from below.
-__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
-  float x0, x1;
-  f2_unpack(x2, x0, x1);
-  x0 = fmaxf(x0, -127.0f);
-  x1 = fmaxf(x1, -127.0f);
-  const uint64_t xc = f2_pack(x0, x1);
-  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);                 // 2^23 + 2^22
-  const uint64_t xr = f2_add_rm(xc, magic);                                  // low mantissa bits = floor(x)
-  const uint64_t fl = f2_sub(xr, magic);
-  const uint64_t fr = f2_sub(xc, fl);                                        // in [0, 1)
-  uint64_t acc = f2_fma(fr, f2_pack(0.077119089663028717f, 0.077119089663028717f),
-                        f2_pack(0.227564394474029541f, 0.227564394474029541f));
-  acc = f2_fma(acc, fr, f2_pack(0.695146143436431885f, 0.695146143436431885f));
-  acc = f2_fma(acc, fr, f2_pack(1.0f, 1.0f));
-  float r0, r1, q0, q1;
-  f2_unpack(xr, r0, r1);
-  f2_unpack(acc, q0, q1);
-  p0 = __int_as_float((__float_as_int(r0) << 23) + __float_as_int(q0));
-  p1 = __int_as_float((__float_as_int(r1) << 23) + __float_as_int(q1));
-}
-
-// NPOLY of the 64 column pairs of a row take the polynomial path, spread evenly.
-template <int NPOLY>
-__host__ __device__ constexpr bool pair_uses_poly(int pi) {
-  return ((pi + 1) * NPOLY) / 64 != (pi * NPOLY) / 64;
-}
+using namespace attn;
 
 // exp2 of NPAIRS column pairs starting at pair PAIR0 of the row (for the poly pattern) held in s[2*i], s[2*i+1];
 // packs P as bf16x2 into pk[i] and accumulates the row sum into l2a/l2b.
@@ -482,10 +421,12 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 }  // namespace
 }  // namespace vgpa
 
+namespace vgpa { int launch_attention_d128(const vgpa_attention_args* a, cudaStream_t stream); }
+
 extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
   using namespace vgpa;
   VGPA_CHECK(a != nullptr, "vgpa_attention_bf16: null args");
-  VGPA_CHECK(a->head_dim == 64, "vgpa_attention_bf16: only head_dim 64 is built (got %d)", a->head_dim);
+  VGPA_CHECK(a->head_dim == 64 || a->head_dim == 128, "vgpa_attention_bf16: head_dim must be 64 or 128 (got %d)", a->head_dim);
   VGPA_CHECK(a->B > 0 && a->H > 0 && a->Sq > 0 && a->Skv > 0, "vgpa_attention_bf16: bad shape B=%d H=%d Sq=%d Skv=%d",
              a->B, a->H, a->Sq, a->Skv);
   VGPA_CHECK(a->q && a->k && a->v && a->out, "vgpa_attention_bf16: null tensor pointer");
@@ -496,9 +437,10 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
   VGPA_CHECK(((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
                reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0,
              "vgpa_attention_bf16: pointers must be 16-byte aligned");
-  const int cols = a->H * 64;
+  const int cols = a->H * a->head_dim;
   VGPA_CHECK(a->q_row_stride >= cols && a->k_row_stride >= cols && a->v_row_stride >= cols && a->out_row_stride >= cols,
-             "vgpa_attention_bf16: row strides must cover H*64 columns");
+             "vgpa_attention_bf16: row strides must cover H*head_dim columns");
+  if (a->head_dim == 128) return launch_attention_d128(a, static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tk, tv;
   const uint32_t box[3] = {64, 128, 1};
   {

@@ -82,7 +82,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
-              out: torch.Tensor | None = None, scale: float = 0.0) -> torch.Tensor:
+              out: torch.Tensor | None = None, scale: float = 0.0, head_dim: int = 64) -> torch.Tensor:
     """softmax(q k^T * scale) v with heads packed along the last dim.
 
     q: [B, Sq, >=heads*64] view, k/v: [B, Skv, >=heads*64] views (last dim contiguous; they may be
@@ -96,11 +96,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
     B, Sq, _ = q.shape
     Skv = k.shape[1]
     if out is None:
-        out = torch.empty((B, Sq, heads * 64), dtype=BF16, device=q.device)
+        out = torch.empty((B, Sq, heads * head_dim), dtype=BF16, device=q.device)
     _req(out, BF16, "out", contiguous=False)
     a = AttentionArgs()
     a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
-    a.B, a.H, a.Sq, a.Skv, a.head_dim = B, heads, Sq, Skv, 64
+    a.B, a.H, a.Sq, a.Skv, a.head_dim = B, heads, Sq, Skv, head_dim
     a.scale = scale
     a.q_row_stride, a.k_row_stride, a.v_row_stride, a.out_row_stride = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
     a.q_batch_stride, a.k_batch_stride, a.v_batch_stride, a.out_batch_stride = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
