@@ -239,6 +239,19 @@ int vgpa_dpo_loss_backward(const vgpa_dpo_args* args, const float* d_grad_loss, 
                            void* stream);
 
 
+/* ------------------------------------------------------------------------------------------------
+ * Wan2.2 DiT helpers (generate/Wan2.2-TI2V-5B.py:120-129). The block itself runs on
+ * vgpa_linear_bf16 / vgpa_attention_bf16 (head_dim 128) / vgpa_layernorm_modulate_bf16.
+ * ---------------------------------------------------------------------------------------------- */
+/* In place on x [rows, ldx]: WanRMSNorm over D columns (`_norm(x.float()).type_as(x) * weight`, weight fp32 [D]) and,
+ * when rope tables are given, the complex-pair rotation of rope_apply on every head (tables [rows_per_sample, head_dim]
+ * fp32, repeat-interleaved cos / sin; rows_per_sample = 0 means rows). */
+int vgpa_rmsnorm_rope_bf16(void* x, int rows, int D, int64_t ldx, const float* weight, float eps, const float* rope_cos,
+                           const float* rope_sin, int head_dim, int rows_per_sample, void* stream);
+/* out[r, :] = bf16(a[r, :] + b[:]) for R rows of N columns (`modulation + e` of WanAttentionBlock / Head); a bf16 with
+ * row stride lda, b fp32. */
+int vgpa_add_rows_bf16(const void* a, const float* b, void* out, int R, int64_t N, int64_t lda, void* stream);
+
 /* ================================================================================================
  * K4 — CogVideoX VAE decoder building blocks. Replace the cuDNN conv3d / GroupNorm / interpolate calls
  * behind diffusers' AutoencoderKLCogVideoX.decode (CogVideoXDecoder3D, CogVideoXResnetBlock3D,
