@@ -100,3 +100,36 @@ def test_wan_denoise_step_vs_oracle(lib):
     ref[:, :1] = lat[:, :1].float()
     assert relmax(nxt, ref) < 3e-2
     assert torch.equal(nxt[:, :1], lat[:, :1].float())
+
+
+def test_wan_lora_merge_vs_oracle(lib, tmp_path):
+    """`--lora_path` for Wan: adapters target q, k, v, o of self_attn and cross_attn (train/Wan2.2-TI2V-5B/03_train.py:82) and the
+    generate script scales alpha/r by --lora_weight 0.2 (generate/Wan2.2-TI2V-5B.py:66-70)."""
+    import json
+    from safetensors.torch import save_file
+    from oracle import dit_torch as OD
+    from videogpa_b200.lora import merge_lora
+    from videogpa_b200.wan import WanConfig, WanTransformer3D
+    kw = _small()
+    ocfg = O.WanConfig(**kw)
+    sd = {k: v.to(BF) for k, v in O.random_state_dict(ocfg, seed=8).items()}
+    model = WanTransformer3D(WanConfig(**kw), sd, device="cuda")
+    D, r = ocfg.dim, 64
+    g = torch.Generator().manual_seed(10)
+    tensors, expect = {}, {}
+    for layer in range(2):
+        for att in ("self_attn", "cross_attn"):
+            for m in "qkvo":
+                A = torch.randn(r, D, generator=g) * 0.05
+                Bm = torch.randn(D, r, generator=g) * 0.05
+                base = f"base_model.model.blocks.{layer}.{att}.{m}"
+                tensors[base + ".lora_A.weight"], tensors[base + ".lora_B.weight"] = A, Bm
+                expect[(layer, f"{att}.{m}")] = OD.lora_merge(sd[f"blocks.{layer}.{att}.{m}.weight"], A, Bm, (128.0 / 64.0) * 0.2)
+    save_file(tensors, str(tmp_path / "adapter_model.safetensors"))
+    (tmp_path / "adapter_config.json").write_text(json.dumps(dict(peft_type="LORA", r=64, lora_alpha=128.0, target_modules=["q", "k", "v", "o"],
+                                                                use_dora=False, use_rslora=False, fan_in_fan_out=False, bias="none")))
+    assert merge_lora(model, str(tmp_path), weight=0.2) == 16
+    for (layer, mod), ref in expect.items():
+        got = model.attention_weight(layer, mod).cpu()
+        diff = (got.float() - ref.float()).abs()
+        assert (got != ref).float().mean() < 0.01 and diff.max() <= 2.0 ** -7 * ref.float().abs().max()

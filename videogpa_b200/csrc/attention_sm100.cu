@@ -421,7 +421,11 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 }  // namespace
 }  // namespace vgpa
 
-namespace vgpa { int launch_attention_d128(const vgpa_attention_args* a, cudaStream_t stream); }
+namespace vgpa {
+int launch_attention_d128(const vgpa_attention_args* a, cudaStream_t stream);
+int launch_attention_d64x4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const vgpa_attention_args* a,
+                           int npoly, cudaStream_t stream);
+}
 
 extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
   using namespace vgpa;
@@ -474,6 +478,13 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
     const char* e = getenv("VGPA_ATTN_NPOLY");
     npoly = e ? atoi(e) : 16;
   }
+  // Development knob: 1 = four softmax warpgroups (attention_d64x4_sm100.cu; same speed, measured), 0 (default) = two (this file).
+  static int x4 = -1;
+  if (x4 < 0) {
+    const char* e = getenv("VGPA_ATTN_X4");
+    x4 = e ? atoi(e) : 0;
+  }
+  if (x4) return launch_attention_d64x4(tq, tk, tv, a, npoly, s);
   switch (npoly) {
     case 0: return launch_attn<0>(tq, tk, tv, prm, grid, s);
     case 32: return launch_attn<32>(tq, tk, tv, prm, grid, s);

@@ -21,6 +21,8 @@ import torch
 from . import dense
 
 _KEY = re.compile(r"(?:base_model\.model\.)?transformer_blocks\.(\d+)\.attn1\.(to_q|to_k|to_v|to_out\.0)\.lora_(A|B)(?:\.default)?\.weight$")
+# Wan2.2 adapters target q, k, v, o of self_attn and cross_attn (train/Wan2.2-TI2V-5B/03_train.py:82)
+_KEY_WAN = re.compile(r"(?:base_model\.model\.)?blocks\.(\d+)\.((?:self|cross)_attn\.[qkvo])\.lora_(A|B)(?:\.default)?\.weight$")
 
 
 def read_adapter(lora_path: str):
@@ -42,7 +44,7 @@ def read_adapter(lora_path: str):
         raise RuntimeError(f"no adapter_model.safetensors under {lora_path}")
     pairs: dict = {}
     for k, v in tensors.items():
-        m = _KEY.search(k)
+        m = _KEY.search(k) or _KEY_WAN.search(k)
         if not m:
             continue
         key = (int(m.group(1)), m.group(2))
@@ -53,7 +55,7 @@ def read_adapter(lora_path: str):
             raise RuntimeError(f"adapter is missing lora_A or lora_B for {key}")
         out[key] = (ab["A"], ab["B"])
     if not out:
-        raise RuntimeError("no attn1 LoRA tensors found in the adapter")
+        raise RuntimeError("no attention LoRA tensors (CogVideoX attn1.* or Wan {self,cross}_attn.*) found in the adapter")
     return cfg, out
 
 
