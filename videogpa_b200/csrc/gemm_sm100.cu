@@ -62,7 +62,7 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 // Epilogue over one 64-column group held in v[64] for output row `row` (may be >= M: no stores).
 template <int EPI>
 __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0, int M,
-                                               const EpiParams& ep) {
+                                               const EpiParams& ep, const uint4 (&res)[8]) {
   const bool live = row < M;
   if (ep.bias != nullptr) {
     const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + col0);
@@ -86,11 +86,10 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
     if (ep.rows_per_sample > 0) { b = row / ep.rows_per_sample; srow = row - b * ep.rows_per_sample; }
     const __nv_bfloat16* g = (srow < ep.text_rows ? ep.gate_txt : ep.gate_vid);
     if (live) {
-      const uint4* rp = reinterpret_cast<const uint4*>(orow);
       const uint4* gp = (g != nullptr) ? reinterpret_cast<const uint4*>(g + b * ep.gate_stride_b + col0) : nullptr;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint4 r = rp[i];
+        const uint4 r = res[i];                          // residual row chunk, prefetched one column group ahead
         uint4 gg = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0
         if (gp != nullptr) gg = __ldg(gp + i);
         const uint32_t ru[4] = {r.x, r.y, r.z, r.w};
@@ -288,12 +287,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
-      ptx::mbar_wait(&tfull_bar[as], aphase);
-      ptx::tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+      // Gated residual: the residual row chunk of column group g+1 is loaded while group g is processed (and group
+      // 0 before the accumulator wait), so the HBM round trip is off the epilogue's critical path. Left to ptxas,
+      // each of the eight 16-byte loads was sunk next to its use behind the previous chunk's store, serialising eight
+      // round trips per group (+1 ms per GEMM at the DiT shapes).
+      uint4 res[8];
+      auto load_res = [&](int g, uint4 (&dst)[8]) {
+        if constexpr (EPI == VGPA_EPI_GATE_RES) {
+          const uint4* rp = reinterpret_cast<const uint4*>(ep.out + static_cast<size_t>(row < M ? row : 0) * ep.ldo + n_blk * BN + g * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = rp[i];
+        }
+      };
+      load_res(0, res);
+      ptx::mbar_wait(&tfull_bar[as], aphase);
+      ptx::tc_fence_after();
 #pragma unroll 1
       for (int g = 0; g < BN / 64; ++g) {
+        uint4 nxt[8];
+        if (g + 1 < BN / 64) load_res(g + 1, nxt);
         uint32_t r0[32], r1[32];
         ptx::tmem_ld_32x32(t_row + g * 64, r0);
         ptx::tmem_ld_32x32(t_row + g * 64 + 32, r1);
@@ -301,7 +315,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[64];
 #pragma unroll
         for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
-        epilogue_group<EPI>(v, row, n_blk * BN + g * 64, M, ep);
+        epilogue_group<EPI>(v, row, n_blk * BN + g * 64, M, ep, res);
+        if constexpr (EPI == VGPA_EPI_GATE_RES) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) res[i] = nxt[i];
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
