@@ -249,3 +249,52 @@ def test_cpu_tensor_is_rejected(lib):
     from videogpa_b200.loss import DPOLoss
     with pytest.raises(RuntimeError):
         DPOLoss()(*[torch.randn(1, 2, 2, 2, 2) for _ in range(6)])
+
+
+# ------------------------------------------------------------------------------------------------ f-1: VideoProcessor
+def _synthetic_da3_predictions(T=5, H=48, W=64, seed=0):
+    rng = np.random.default_rng(seed)
+    depth = (2.0 + 0.5 * rng.random((T, H, W))).astype(np.float32)
+    conf = (1.0 + rng.random((T, H, W))).astype(np.float32)
+    images = rng.random((T, H, W, 3)).astype(np.float32)                                   # processed_images are THWC
+    K = np.tile(np.array([[0.8 * W, 0, W / 2], [0, 0.8 * W, H / 2], [0, 0, 1]], dtype=np.float32), (T, 1, 1))
+    E = np.zeros((T, 3, 4), dtype=np.float32)
+    for i in range(T):
+        a = math.radians(0.7 * i)
+        E[i] = np.array([[math.cos(a), 0, math.sin(a), 0.03 * i], [0, 1, 0, 0.0], [-math.sin(a), 0, math.cos(a), 0.01 * i]], dtype=np.float32)
+    return dict(depth=depth, depth_conf=conf, images=images, intrinsic=K, extrinsic=E)
+
+
+def test_video_processor_da3_path_vs_oracle_composition(lib):
+    """pipelines/process_video.py:100-196 from the predictions onwards: un-project, point cloud per threshold, reprojection,
+    metric dispatch — against the same chain built from the oracle functions."""
+    from videogpa_b200.metrics import Consistency_Score, MSEMetric, MVCSMetric
+    from videogpa_b200.process_video import VideoProcessor
+    preds = _synthetic_da3_predictions()
+    lp = lambda a, b: (a - b).abs().mean(dim=(1, 2, 3))                                     # stand-in for the LPIPS-VGG callable
+    vp = VideoProcessor({"Consistency_Score": Consistency_Score(lpips_net=lp), "MVCS": MVCSMetric(), "MSE": MSEMetric()},
+                        model_name="depth-anything/DA3-LARGE")
+    assert vp.backbone == "da3"
+    res = vp.process_predictions(preds, thresholds=[0, 40])
+    assert set(res) == {0, 40, "_extrinsic"} and np.allclose(np.array(res["_extrinsic"]), preds["extrinsic"])
+    T, H, W = preds["depth"].shape
+    imgs = np.ascontiguousarray(preds["images"].transpose(0, 3, 1, 2))
+    world = o.unproject_depth(preds["depth"], preds["intrinsic"], preds["extrinsic"])
+    for th in (0, 40):
+        verts, cols, _ = o.get_colored_pointcloud(world.reshape(-1, 3), preds["depth_conf"].reshape(-1), imgs, conf_thres=float(th))
+        rep = o.batch_reproject(verts, cols, preds["intrinsic"], preds["extrinsic"], H, W)
+        want_mse = o.mse_metric(imgs, rep)
+        want_lp = float(np.abs((imgs * 2 - 1) - rep).mean())
+        assert abs(res[th]["MSE"] - want_mse) <= 1e-5 * max(1.0, want_mse)
+        assert abs(res[th]["Consistency_Score"] - (want_mse + want_lp)) <= 2e-5 * max(1.0, want_mse + want_lp)
+        assert abs(res[th]["motion_norm"] - o.motion_score(preds["extrinsic"])) <= 1e-6
+        assert abs(res[th]["MVCS"] - o.mvcs(preds["depth"], preds["intrinsic"], preds["extrinsic"])) <= 1e-9
+    assert res[0]["MVCS"] == res[40]["MVCS"]                                                # MVCS ignores the threshold
+    # additive batched API: one launch for many clips, result stays on the device
+    d = torch.from_numpy(preds["depth"]).cuda()[None].repeat(3, 1, 1, 1)
+    sc = vp.process_batch(d, torch.from_numpy(preds["intrinsic"])[None].repeat(3, 1, 1, 1), torch.from_numpy(preds["extrinsic"])[None].repeat(3, 1, 1, 1))
+    assert sc.is_cuda and sc.shape == (3,) and abs(sc[1].item() - res[0]["MVCS"]) <= 1e-12
+    # backbone resolution rules (pipelines/process_video.py:31-41) and the injected-backbone contract
+    assert VideoProcessor({}, backbone="VGGT").backbone == "vggt" and VideoProcessor({}).backbone == "vggt"
+    with pytest.raises(RuntimeError):
+        VideoProcessor({}).process("x.mp4", [0], 10)

@@ -1,0 +1,44 @@
+"""Dev (2 GPUs, torchrun): CFG-pair sharding of one CogVideoX denoise step over NCCL vs the single-GPU batched pair.
+Ranks (0, 1) run the uncond / cond branch, exchange the noise prediction with one all-gather and apply the same update."""
+import os, sys
+import torch
+import torch.distributed as dist
+sys.path.insert(0, ".")
+from videogpa_b200.parallel import CfgPairGroup, init_from_env
+from videogpa_b200.pipeline import CogVideoXDenoisePipeline
+from videogpa_b200.schedulers import CogVideoXDDIMScheduler
+from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+
+rank, world, local = init_from_env("nccl")
+dev = torch.device("cuda", local)
+layers = int(os.environ.get("LAYERS", "42"))
+cfg = TransformerConfig.cogvideox_5b(); cfg.num_layers = layers
+model = CogVideoXTransformer3D.random_init(cfg, seed=1234, device=dev)
+sched = CogVideoXDDIMScheduler(); ts = sched.set_timesteps(50)
+pipe = CogVideoXDenoisePipeline(model, sched)
+lat = pipe.prepare_latents(1, 49, 480, 720, generator=torch.Generator(device=dev).manual_seed(42))
+pe = torch.randn(2, 226, 4096, device=dev, generator=torch.Generator(device=dev).manual_seed(43)).to(torch.bfloat16)
+rope = pipe.rotary(13, 60, 90)
+group = CfgPairGroup(rank, world)
+def run(g, n=3):
+    x = lat
+    for i in range(2):
+        x = pipe.denoise_step(x, pe, int(ts[i]), 6.0, rope, cfg_group=g)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        x = pipe.denoise_step(x, pe, int(ts[2 + i]), 6.0, rope, cfg_group=g)
+    e1.record(); torch.cuda.synchronize()
+    return x, e0.elapsed_time(e1) / n
+x_pair, ms_pair = run(group)
+x_single, ms_single = run(None)
+same = bool(torch.equal(x_pair, x_single))
+both = [torch.empty_like(x_pair) for _ in range(world)]
+dist.all_gather(both, x_pair)
+ident = bool(torch.equal(both[0], both[1]))
+t = torch.tensor([ms_pair, ms_single], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f"CFG-pair shard over 2 GPUs ({layers} layers): {t[0].item():.1f} ms/step vs {t[1].item():.1f} ms/step batched on one GPU "
+          f"(speed-up {t[1].item()/t[0].item():.2f}x); latents identical across the pair: {ident}; identical to the single-GPU batched step: {same}")
+dist.destroy_process_group()

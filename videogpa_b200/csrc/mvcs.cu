@@ -108,9 +108,11 @@ mvcs_pairs_kernel(const float* __restrict__ depths, const float* __restrict__ pa
   const int pair_i = blockIdx.y;        // 0..T-2
   const int clip = blockIdx.z;
   const long long pair_idx = static_cast<long long>(clip) * (T - 1) + pair_i;
-  __shared__ float sp[MV_PAIR_FLOATS];
-  if (threadIdx.x < MV_PAIR_FLOATS) sp[threadIdx.x] = pairs[pair_idx * MV_PAIR_FLOATS + threadIdx.x];
-  __syncthreads();
+  // the 30 pair constants live in registers (the kernel is issue-bound: ~200 instructions per pixel, most of them the
+  // reference's fp32 operation order without FMA contraction and four IEEE divisions)
+  float sp[MV_PAIR_FLOATS - 2];
+#pragma unroll
+  for (int k = 0; k < MV_PAIR_FLOATS - 2; ++k) sp[k] = __ldg(pairs + pair_idx * MV_PAIR_FLOATS + k);
   const float* di = depths + (static_cast<long long>(clip) * T + pair_i) * H * W;
   const float* dj = di + static_cast<long long>(H) * W;
   const int HW = H * W;
@@ -128,11 +130,14 @@ mvcs_pairs_kernel(const float* __restrict__ depths, const float* __restrict__ pa
 #pragma unroll
       for (int k = 0; k < MV_PIX_PER_THREAD; ++k) d4[k] = (base + k < HW) ? di[base + k] : 0.f;
     }
+    const bool one_row = (W & 3) == 0;                    // 4 consecutive pixels never straddle a row
+    const int py0 = base / W, px0 = base - py0 * W;
 #pragma unroll
     for (int k = 0; k < MV_PIX_PER_THREAD; ++k) {
       const int pix = base + k;
       if (pix >= HW) break;
-      const int py = pix / W, px = pix - py * W;
+      int py = py0, px = px0 + k;
+      if (!one_row && px >= W) { py = pix / W; px = pix - py * W; }
       const float u = static_cast<float>(px), v = static_cast<float>(py), d = d4[k];
       // p_i = (K_i^-1 @ [u, v, 1]) * d          (mvcs.py:64-66)
       const float xi = ((sp[0] * u + sp[1] * v) + sp[2]) * d;
