@@ -54,15 +54,21 @@ class _Base:
         return int(t) - self.num_train_timesteps // self.num_inference_steps
 
     # training-side helpers (03_train.py:129-130,154-155); plain fp32 tensor math on the caller's device
-    def add_noise(self, x, noise, timesteps):
-        a = torch.as_tensor(self.alphas_cumprod[np.asarray(timesteps.cpu())], dtype=x.dtype, device=x.device)
+    def _sqrt_coeffs(self, x, timesteps):
+        """sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t) taken in float64 on the host table, then cast to x's dtype."""
+        a = self.alphas_cumprod[np.asarray(timesteps.cpu())]
         shp = (-1,) + (1,) * (x.dim() - 1)
-        return a.sqrt().view(shp) * x + (1 - a).sqrt().view(shp) * noise
+        sa = torch.as_tensor(np.sqrt(a), dtype=x.dtype, device=x.device).view(shp)
+        sb = torch.as_tensor(np.sqrt(1.0 - a), dtype=x.dtype, device=x.device).view(shp)
+        return sa, sb
+
+    def add_noise(self, x, noise, timesteps):
+        sa, sb = self._sqrt_coeffs(x, timesteps)
+        return sa * x + sb * noise
 
     def get_velocity(self, x, noise, timesteps):
-        a = torch.as_tensor(self.alphas_cumprod[np.asarray(timesteps.cpu())], dtype=x.dtype, device=x.device)
-        shp = (-1,) + (1,) * (x.dim() - 1)
-        return a.sqrt().view(shp) * noise - (1 - a).sqrt().view(shp) * x
+        sa, sb = self._sqrt_coeffs(x, timesteps)
+        return sa * noise - sb * x
 
 
 class CogVideoXDDIMScheduler(_Base):
