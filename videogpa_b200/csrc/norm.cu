@@ -82,30 +82,27 @@ ln_modulate_kernel(LnParams p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16x2(bv[k]); y[2 * k] += f.x; y[2 * k + 1] += f.y; }
     }
+    // eager bf16 semantics with packed bf16x2 hardware ops (one rounding per op, exactly what torch's bf16 kernels do):
+    // n = bf16(LN(x));  n = n * bf16(1 + scale);  n = n + shift
+    __nv_bfloat162 nb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nb[k] = __floats2bfloat162_rn(y[2 * k], y[2 * k + 1]);
     if (sc4) {
-      // eager bf16: n = LN(x) (rounded); n * (1 + scale) (both rounded); + shift (rounded)
       const uint4 su = __ldg(sc4 + idx);
       const uint32_t sv[4] = {su.x, su.y, su.z, su.w};
+      const __nv_bfloat162 one = __floats2bfloat162_rn(1.0f, 1.0f);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(sv[k]);
-        y[2 * k] = bf16_round(bf16_round(y[2 * k]) * bf16_round(1.0f + f.x));
-        y[2 * k + 1] = bf16_round(bf16_round(y[2 * k + 1]) * bf16_round(1.0f + f.y));
-      }
+      for (int k = 0; k < 4; ++k) nb[k] = __hmul2(nb[k], __hadd2(one, *reinterpret_cast<const __nv_bfloat162*>(&sv[k])));
     }
     if (sh4) {
       const uint4 su = __ldg(sh4 + idx);
       const uint32_t sv[4] = {su.x, su.y, su.z, su.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(sv[k]);
-        y[2 * k] = bf16_round(y[2 * k]) + f.x;
-        y[2 * k + 1] = bf16_round(y[2 * k + 1]) + f.y;
-      }
+      for (int k = 0; k < 4; ++k) nb[k] = __hadd2(nb[k], *reinterpret_cast<const __nv_bfloat162*>(&sv[k]));
     }
     uint4 o;
-    o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-    o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&nb[0]); o.y = *reinterpret_cast<uint32_t*>(&nb[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&nb[2]); o.w = *reinterpret_cast<uint32_t*>(&nb[3]);
     orow[idx] = o;
   }
 }
