@@ -28,6 +28,7 @@ class DiTConfig:
     text_embed_dim: int = 4096
     num_layers: int = 42
     patch_size: int = 2
+    patch_size_t: int | None = None      # CogVideoX1.5: 2 (Linear patch embed over (c, pt, ph, pw), no patch bias)
     sample_width: int = 90
     sample_height: int = 60
     sample_frames: int = 49
@@ -63,7 +64,10 @@ def random_state_dict(cfg: DiTConfig, seed: int = 1234, dtype=torch.float32, std
         sd[name + ".bias"] = (0.05 * torch.randn(n, generator=g)) if randomize_norms else torch.zeros(n)
 
     p = cfg.patch_size
-    sd["patch_embed.proj.weight"] = torch.randn(D, cfg.in_channels, p, p, generator=g) * std
+    if cfg.patch_size_t is None:
+        sd["patch_embed.proj.weight"] = torch.randn(D, cfg.in_channels, p, p, generator=g) * std
+    else:
+        sd["patch_embed.proj.weight"] = torch.randn(D, cfg.in_channels * cfg.patch_size_t * p * p, generator=g) * std
     sd["patch_embed.proj.bias"] = (torch.randn(D, generator=g) * std) if randomize_norms else torch.zeros(D)
     lin("patch_embed.text_proj", D, cfg.text_embed_dim)
     if cfg.use_learned_positional_embeddings:
@@ -83,7 +87,7 @@ def random_state_dict(cfg: DiTConfig, seed: int = 1234, dtype=torch.float32, std
         lin(b + "ff.net.2", D, cfg.ffn_mult * D)
     norm("norm_final", D)
     lin("norm_out.linear", 2 * D, Tm); norm("norm_out.norm", D)
-    lin("proj_out", p * p * cfg.out_channels, D)
+    lin("proj_out", p * p * (cfg.patch_size_t or 1) * cfg.out_channels, D)
     return {k: v.to(dtype) for k, v in sd.items()}
 
 
@@ -167,8 +171,14 @@ def transformer_forward(sd: dict, cfg: DiTConfig, hidden_states: torch.Tensor, e
     t_emb = timestep_embedding(timestep, D).to(dtype)
     emb = F.linear(t_emb, sd["time_embedding.linear_1.weight"], sd["time_embedding.linear_1.bias"])
     emb = F.linear(F.silu(emb), sd["time_embedding.linear_2.weight"], sd["time_embedding.linear_2.bias"])
-    x_img = F.conv2d(hidden_states.reshape(B * Fr, C, H, W).to(dtype), sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=p)
-    x_img = x_img.view(B, Fr, D, H // p, W // p).flatten(3).transpose(2, 3).flatten(1, 2)
+    pt = cfg.patch_size_t
+    if pt is None:
+        x_img = F.conv2d(hidden_states.reshape(B * Fr, C, H, W).to(dtype), sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=p)
+        x_img = x_img.view(B, Fr, D, H // p, W // p).flatten(3).transpose(2, 3).flatten(1, 2)
+    else:                                                         # CogVideoXPatchEmbed with patch_size_t (1.5)
+        e = hidden_states.to(dtype).reshape(B, Fr // pt, pt, C, H // p, p, W // p, p)
+        e = e.permute(0, 1, 4, 6, 3, 2, 5, 7).flatten(4, 7).flatten(1, 3)
+        x_img = F.linear(e, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"])
     x_txt = F.linear(encoder_hidden_states.to(dtype), sd["patch_embed.text_proj.weight"], sd["patch_embed.text_proj.bias"])
     x = torch.cat([x_txt, x_img], dim=1)
     if cfg.use_learned_positional_embeddings:
@@ -198,7 +208,11 @@ def transformer_forward(sd: dict, cfg: DiTConfig, hidden_states: torch.Tensor, e
     shift, scale = mod.chunk(2, dim=1)
     hs = F.layer_norm(hs, (D,), sd["norm_out.norm.weight"], sd["norm_out.norm.bias"], cfg.norm_eps) * (1 + scale)[:, None, :] + shift[:, None, :]
     hs = F.linear(hs, sd["proj_out.weight"], sd["proj_out.bias"])
-    out = hs.reshape(B, Fr, H // p, W // p, -1, p, p).permute(0, 1, 4, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)
+    if pt is None:
+        out = hs.reshape(B, Fr, H // p, W // p, -1, p, p).permute(0, 1, 4, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)
+    else:
+        out = hs.reshape(B, (Fr + pt - 1) // pt, H // p, W // p, -1, pt, p, p)
+        out = out.permute(0, 1, 5, 4, 2, 6, 3, 7).flatten(6, 7).flatten(4, 5).flatten(1, 2)
     return out
 
 

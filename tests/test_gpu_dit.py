@@ -94,7 +94,7 @@ def _small_cfg(**kw):
     return base
 
 
-@pytest.mark.parametrize("variant", ["t2v_rope", "train_no_rope", "i2v_posemb"])
+@pytest.mark.parametrize("variant", ["t2v_rope", "train_no_rope", "i2v_posemb", "v1_5_temporal_patch"])
 def test_transformer_forward_vs_oracle(lib, variant):
     """Whole-model parity on a small config with the true block structure (rope / no-rope training call / I2V)."""
     from videogpa_b200.rope import get_3d_rotary_pos_embed
@@ -102,21 +102,24 @@ def test_transformer_forward_vs_oracle(lib, variant):
     kw = _small_cfg()
     if variant == "i2v_posemb":
         kw.update(in_channels=32, use_learned_positional_embeddings=True)
+    if variant == "v1_5_temporal_patch":
+        kw.update(patch_size_t=2)
     ocfg = O.DiTConfig(**kw)
     sd = O.random_state_dict(ocfg, seed=7, randomize_norms=True, std=0.05)
     sd = {k: v.to(BF).float() for k, v in sd.items()}                 # oracle and kernels see the same bf16 weights
     model = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
-    B, Fr, C, H, W, St = 2, 3, kw.get("in_channels", 16), 16, 24, 18
+    B, Fr, C, H, W, St = 2, (4 if variant == "v1_5_temporal_patch" else 3), kw.get("in_channels", 16), 16, 24, 18
+    Fr_rope = Fr // 2 if variant == "v1_5_temporal_patch" else Fr
     g = torch.Generator().manual_seed(3)
     hs = torch.randn(B, Fr, C, H, W, generator=g).to(BF).float()
     enc = torch.randn(B, St, 256, generator=g).to(BF).float()
     t = torch.tensor([999, 499])
-    rope = None if variant == "train_no_rope" else O.rope_3d(ocfg, Fr, H, W)
+    rope = None if variant == "train_no_rope" else O.rope_3d(ocfg, Fr_rope, H, W)
     ref = O.transformer_forward(sd, ocfg, hs, enc, t, rope)
     if variant == "train_no_rope":       # positional call form of 03_train.py:134-139
         out = model(hs.cuda(), encoder_hidden_states=enc.cuda(), timestep=t.cuda(), return_dict=True).sample
     else:
-        mine = get_3d_rotary_pos_embed(64, H // 2, W // 2, Fr)
+        mine = get_3d_rotary_pos_embed(64, H // 2, W // 2, Fr_rope)
         assert torch.equal(mine[0], rope[0]) and torch.equal(mine[1], rope[1])
         out = model(hidden_states=hs.cuda(), encoder_hidden_states=enc.cuda(), timestep=t.cuda(), image_rotary_emb=mine,
                     return_dict=False)[0]
@@ -209,3 +212,22 @@ def test_generate_cli_synthetic_end_to_end(lib, tmp_path, capsys):
     g.main(argv)
     second = capsys.readouterr().out
     assert second.count("Skip existing") == 2
+
+
+def test_generate_cli_1_5_synthetic(lib, tmp_path, capsys):
+    """generate/CogVideoX1.5-5B.py surface: extra flags / defaults (:102-111), temporal patching end to end
+    (9 frames -> 3 latent frames, padded to 4 and the extra leading frame dropped before decoding), dynamic CFG."""
+    import json
+    from videogpa_b200.generate import cogvideox1_5_5b as g
+    a = g.build_parser().parse_args(["--prompt_json", "x", "--output_dir", "y"])
+    assert (a.base_model, a.lora_weight, a.height, a.width, a.num_frames, a.fps) == ("THUDM/CogVideoX1.5-5B", 0.2, 768, 1360, 81, 16)
+    pj = tmp_path / "p.json"
+    pj.write_text(json.dumps([{"group_id": "g0", "text_prompt": "a green pyramid"}]))
+    out = tmp_path / "out"
+    g.main(["--prompt_json", str(pj), "--output_dir", str(out), "--synthetic", "1", "--num_inference_steps", "2",
+            "--num_frames", "9", "--height", "96", "--width", "160"])
+    txt = capsys.readouterr().out
+    assert "Failed" not in txt, txt
+    import cv2
+    cap = cv2.VideoCapture(str(out / "g0" / "seed_42.mp4"))
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 9 and int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == 160

@@ -51,8 +51,9 @@ class CogVideoXDenoisePipeline:
         c = self.transformer.config
         if not c.use_rotary_positional_embeddings:
             return None
+        pt = getattr(c, "patch_size_t", None) or 1                      # 1.5: one rotary position per temporal patch
         return get_3d_rotary_pos_embed(c.attention_head_dim, latent_h // c.patch_size, latent_w // c.patch_size,
-                                       latent_frames, device=self.device)
+                                       (latent_frames + pt - 1) // pt, device=self.device)
 
     @staticmethod
     def dynamic_guidance(guidance_scale: float, num_inference_steps: int, t: int) -> float:
@@ -103,8 +104,13 @@ class CogVideoXDenoisePipeline:
         pe = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0).to(device=self.device, dtype=BF16).contiguous()
         B = prompt_embeds.shape[0]
         timesteps = self.scheduler.set_timesteps(num_inference_steps)
+        # CogVideoX1.5 (patch_size_t = 2): the latent frame count is padded to a multiple of the temporal patch by generating
+        # extra leading frames, which are dropped before decoding (diffusers CogVideoXPipeline.__call__, App. A.4)
+        pt = getattr(self.transformer.config, "patch_size_t", None) or 1
+        latent_frames = (num_frames - 1) // self.vae_scale_factor_temporal + 1
+        additional_frames = (pt - latent_frames % pt) % pt
         if latents is None:
-            latents = self.prepare_latents(B, num_frames, height, width, generator)
+            latents = self.prepare_latents(B, num_frames + additional_frames * self.vae_scale_factor_temporal, height, width, generator)
         latents = latents.to(device=self.device, dtype=BF16).contiguous()
         rope = self.rotary(latents.shape[1], latents.shape[3], latents.shape[4])
         if image_latents is not None:
@@ -115,6 +121,8 @@ class CogVideoXDenoisePipeline:
                                         cfg_group=cfg_group)
             if callback is not None:
                 callback(i, int(t), latents)
+        if additional_frames:
+            latents = latents[:, additional_frames:]
         if output_type == "latent" or self.vae is None:
             return latents
         # decode: latents [B,F,C,H,W] -> [B,C,F,H,W] / scaling_factor (App. A.4)

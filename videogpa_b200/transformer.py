@@ -36,6 +36,7 @@ class TransformerConfig:
     text_embed_dim: int = 4096
     num_layers: int = 42
     patch_size: int = 2
+    patch_size_t: int | None = None      # CogVideoX1.5: 2 (Linear patch embed over (c, pt, ph, pw))
     sample_width: int = 90
     sample_height: int = 60
     sample_frames: int = 49
@@ -57,6 +58,11 @@ class TransformerConfig:
     @classmethod
     def cogvideox_5b_i2v(cls) -> "TransformerConfig":
         return cls(in_channels=32, use_learned_positional_embeddings=True)
+
+    @classmethod
+    def cogvideox1_5_5b(cls) -> "TransformerConfig":
+        """CogVideoX1.5-5B T2V (generate/CogVideoX1.5-5B.py: 81 frames 1360x768): temporal patching, 224 text tokens."""
+        return cls(patch_size_t=2, sample_width=170, sample_height=96, sample_frames=81, max_text_seq_length=224)
 
 
 class Transformer3DOutput(SimpleNamespace):
@@ -98,7 +104,10 @@ class CogVideoXTransformer3D:
             sd[name + ".weight"] = torch.ones(n, device=dev, dtype=BF16)
             sd[name + ".bias"] = torch.zeros(n, device=dev, dtype=BF16)
 
-        sd["patch_embed.proj.weight"] = (torch.randn(D, config.in_channels, p, p, generator=g, device=dev) * std).to(BF16)
+        if config.patch_size_t is None:
+            sd["patch_embed.proj.weight"] = (torch.randn(D, config.in_channels, p, p, generator=g, device=dev) * std).to(BF16)
+        else:
+            sd["patch_embed.proj.weight"] = (torch.randn(D, config.in_channels * config.patch_size_t * p * p, generator=g, device=dev) * std).to(BF16)
         sd["patch_embed.proj.bias"] = torch.zeros(D, device=dev, dtype=BF16)
         lin("patch_embed.text_proj", D, config.text_embed_dim)
         if config.use_learned_positional_embeddings:
@@ -118,7 +127,7 @@ class CogVideoXTransformer3D:
             lin(b + "ff.net.2", D, config.ffn_mult * D)
         norm("norm_final", D)
         lin("norm_out.linear", 2 * D, Tm); norm("norm_out.norm", D)
-        lin("proj_out", p * p * config.out_channels, D)
+        lin("proj_out", p * p * (config.patch_size_t or 1) * config.out_channels, D)
         return cls(config, sd, device=dev)
 
     def _load(self, sd: dict) -> None:
@@ -134,7 +143,13 @@ class CogVideoXTransformer3D:
             return sd[name].to(device=dev, dtype=torch.float32).contiguous()
 
         self.patch_w = w("patch_embed.proj.weight").reshape(D, -1).contiguous()          # [D, C*p*p], (c, ph, pw) order
-        self.patch_b = w("patch_embed.proj.bias")
+        self.patch_b = w("patch_embed.proj.bias") if "patch_embed.proj.bias" in sd else torch.zeros(D, device=dev, dtype=BF16)
+        pt = c.patch_size_t
+        if pt is not None:
+            # 1.5: features are (c, pt, ph, pw); the per-frame patchify kernel produces (c, ph, pw) per frame, so the two
+            # frames of a temporal patch are concatenated as (pt, c, ph, pw) and the weight columns are permuted to match
+            pp = c.patch_size ** 2
+            self.patch_w = self.patch_w.view(D, c.in_channels, pt, pp).permute(0, 2, 1, 3).reshape(D, -1).contiguous()
         self.text_w, self.text_b = w("patch_embed.text_proj.weight"), w("patch_embed.text_proj.bias")
         self.pos_embedding = w("patch_embed.pos_embedding") if c.use_learned_positional_embeddings else None
         self.t1_w, self.t1_b = w("time_embedding.linear_1.weight"), w("time_embedding.linear_1.bias")
@@ -159,6 +174,10 @@ class CogVideoXTransformer3D:
         self.no_lw, self.no_lb = w("norm_out.linear.weight"), w("norm_out.linear.bias")
         self.no_w, self.no_b = w("norm_out.norm.weight"), w("norm_out.norm.bias")
         self.po_w, self.po_b = w("proj_out.weight"), w("proj_out.bias")
+        if pt is not None:
+            pp, Co = c.patch_size ** 2, c.out_channels
+            self.po_w = self.po_w.view(Co, pt, pp, D).permute(1, 0, 2, 3).reshape(-1, D).contiguous()
+            self.po_b = self.po_b.view(Co, pt, pp).permute(1, 0, 2).reshape(-1).contiguous()
 
     # ------------------------------------------------------------------ nn.Module-ish surface the callers touch
     def eval(self):
@@ -201,7 +220,11 @@ class CogVideoXTransformer3D:
         hs = hidden_states.to(device=dev, dtype=BF16).contiguous()
         enc_in = encoder_hidden_states.to(device=dev, dtype=BF16).contiguous()
         St = enc_in.shape[1]
-        Sv = Fr * (H // p) * (W // p)
+        pt = c.patch_size_t or 1
+        if Fr % pt != 0:
+            raise RuntimeError(f"the number of latent frames ({Fr}) must be a multiple of patch_size_t ({pt}); the pipeline pads it")
+        hw = (H // p) * (W // p)
+        Sv = (Fr // pt) * hw
         S = St + Sv
         ts = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32)
         if ts.numel() == 1 and B > 1:
@@ -214,7 +237,9 @@ class CogVideoXTransformer3D:
 
         # patch embed: [text_proj(enc) ; proj(2x2 patches)] (+ learned positional embedding for I2V)
         x = torch.empty((B, S, D), dtype=BF16, device=dev)
-        patches = dense.patchify(hs.view(B * Fr, C, H, W))
+        patches = dense.patchify(hs.view(B * Fr, C, H, W))                                   # [B*Fr*hw, C*p*p]
+        if pt > 1:                                                                            # [B, Fr/pt, pt, hw, Cpp] -> [.., hw, pt*Cpp]
+            patches = patches.view(B, Fr // pt, pt, hw, -1).permute(0, 1, 3, 2, 4).reshape(B * Sv, -1).contiguous()
         epi = dense.EPI_BIAS
         if self.pos_embedding is not None:
             if self.pos_embedding.shape[1] < S:
@@ -229,7 +254,7 @@ class CogVideoXTransformer3D:
         if image_rotary_emb is not None:
             cos, sin = image_rotary_emb
             rope = (cos.to(device=dev, dtype=torch.float32).contiguous(), sin.to(device=dev, dtype=torch.float32).contiguous())
-            if rope[0].shape != (Sv, 64):
+            if tuple(rope[0].shape) != (Sv, 64):
                 raise RuntimeError(f"image_rotary_emb must be ([{Sv}, 64], [{Sv}, 64]), got {tuple(rope[0].shape)}")
 
         x2 = x.view(B * S, D)
@@ -267,9 +292,11 @@ class CogVideoXTransformer3D:
                                      scale_txt=mo[:, D:2 * D], mod_stride_b=2 * D)
         y3 = y.view(B, S, D)
         pd = p * p * c.out_channels
-        tok = torch.empty((B * Sv, pd), dtype=BF16, device=dev)
+        tok = torch.empty((B * Sv, pt * pd), dtype=BF16, device=dev)
         for b in range(B):
             dense.linear(y3[b, St:], self.po_w, self.po_b, out=tok[b * Sv:(b + 1) * Sv])
+        if pt > 1:                                                                            # [.., hw, pt, pd] -> one row per (frame, patch)
+            tok = tok.view(B, Fr // pt, hw, pt, pd).permute(0, 1, 3, 2, 4).reshape(B * Fr * hw, pd).contiguous()
         out = dense.unpatchify(tok, B * Fr, c.out_channels, H, W).view(B, Fr, c.out_channels, H, W)
         if not return_dict:
             return (out,)
