@@ -231,3 +231,21 @@ def test_generate_cli_1_5_synthetic(lib, tmp_path, capsys):
     import cv2
     cap = cv2.VideoCapture(str(out / "g0" / "seed_42.mp4"))
     assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 9 and int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == 160
+
+
+def test_generate_cli_i2v_synthetic(lib, tmp_path, capsys):
+    """generate/CogVideoX-5B-I2V.py surface on the GPU: first-frame latent channel-concat (in_channels 32 + learned positional
+    embedding), `--base_dir` image resolution, missing image -> skipped, item without image -> ignored."""
+    import json
+    from videogpa_b200.generate import cogvideox_5b_i2v as g
+    (tmp_path / "imgs").mkdir()
+    (tmp_path / "imgs" / "a.png").write_bytes(b"not really a png, only hashed in synthetic mode")
+    pj = tmp_path / "p.json"
+    pj.write_text(json.dumps({"s1": {"text_prompt": "a boat", "image_prompt": "a.png"}, "s2": {"text_prompt": "a car", "image_prompt": "missing.png"},
+                              "s3": {"text_prompt": "no image"}}))
+    out = tmp_path / "out"
+    g.main(["--prompt_json", str(pj), "--output_dir", str(out), "--base_dir", str(tmp_path / "imgs"), "--synthetic", "1",
+            "--num_inference_steps", "2", "--num_frames", "9", "--height", "96", "--width", "160"])
+    txt = capsys.readouterr().out
+    assert "Failed" not in txt and "Image not found" in txt, txt
+    assert (out / "s1" / "seed_42.mp4").exists() and not (out / "s2").exists() and not (out / "s3").exists()

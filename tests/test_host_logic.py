@@ -194,3 +194,25 @@ def test_generate_cli_surface_and_task_parsing(tmp_path):
     assert g.video_path_for(tmp_path, tasks[0], 0, 1)[0] == "7" and g.video_path_for(tmp_path, tasks[1], 1, 1)[0] == "1"
     f.write_text("3")
     assert g.load_tasks(str(f), None) is None
+
+
+def test_generate_cli_i2v_and_1_5_surfaces(tmp_path):
+    """Flag surfaces of the I2V and 1.5 generate CLIs (generate/CogVideoX-5B-I2V.py:100-112, generate/CogVideoX1.5-5B.py:102-111)
+    and the I2V task / image resolution rules (host logic only)."""
+    import json
+    from videogpa_b200.generate import cogvideox1_5_5b as g15
+    from videogpa_b200.generate import cogvideox_5b_i2v as gi
+    a = gi.build_parser().parse_args(["--prompt_json", "p", "--output_dir", "o", "--base_dir", "imgs"])
+    assert (a.base_model, a.base_dir, a.seed, a.num_inference_steps, a.guidance_scale, a.fps) == ("THUDM/CogVideoX-5B-I2V", "imgs", 42, 50, 6.0, 8)
+    b = g15.build_parser().parse_args(["--prompt_json", "p", "--output_dir", "o"])
+    assert (b.lora_weight, b.height, b.width, b.num_frames, b.fps) == (0.2, 768, 1360, 81, 16)
+    f = tmp_path / "p.json"
+    f.write_text(json.dumps({"k1": {"text_prompt": "a", "image_prompt": "a.png"}, "k2": {"prompt": "b", "image_path": "b.png"}}))
+    tasks = gi.load_tasks(str(f), None)
+    assert [t[0] for t in tasks] == ["k1", "k2"] and gi.load_tasks(str(f), 1) == tasks[:1]
+    (tmp_path / "imgs").mkdir()
+    (tmp_path / "imgs" / "a.png").write_bytes(b"x")
+    assert gi.resolve_image(tasks[0][1], str(tmp_path / "imgs")) == str(tmp_path / "imgs" / "a.png")
+    assert gi.resolve_image(tasks[1][1], None) == "b.png" and gi.resolve_image({}, None) == ""
+    f.write_text(json.dumps([{"group_id": 3, "text_prompt": "x", "input_image_path": "c.png"}]))
+    assert gi.load_tasks(str(f), None)[0][0] == 3

@@ -1,0 +1,143 @@
+"""`generate/CogVideoX-5B-I2V.py` of the reference on the sm_100a kernels — same flags.
+
+Reference: generate/CogVideoX-5B-I2V.py:12-115: the T2V flags plus `--base_dir` (root for relative image paths); tasks are
+`(group_id, {text_prompt, image_prompt | image_path | input_image_path})`; items without a prompt or an image are
+skipped, a missing image prints `Image not found ... skipping`; the checkpoint's default (DDIM) scheduler is kept.
+The I2V transformer (in_channels 32, learned positional embedding) and the channel-concat of the encoded first frame run
+on videogpa_b200 kernels. The first-frame latent comes from the VAE *encoder*, which is a "next" row
+and not built: with a real checkpoint the CLI looks for a pre-computed `<image>.latent.pt` ([16, 1, h, w], already
+multiplied by scaling_factor) next to the image; `--synthetic N` derives a hash-seeded latent from the image bytes so the
+CLI contract can be exercised without checkpoints.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+from pathlib import Path
+
+import torch
+
+from . import cogvideox_5b as base
+
+
+def load_tasks(prompt_json: str, num_prompts: int | None):
+    """generate/CogVideoX-5B-I2V.py:36-48."""
+    with open(prompt_json, "r", encoding="utf-8") as f:
+        raw = json.load(f)
+    if isinstance(raw, dict):
+        tasks = list(raw.items())
+    elif isinstance(raw, list):
+        tasks = [(item.get("group_id", i), item) for i, item in enumerate(raw)]
+    else:
+        return None
+    return tasks[:num_prompts] if num_prompts else tasks
+
+
+def resolve_image(item: dict, base_dir: str | None) -> str:
+    """generate/CogVideoX-5B-I2V.py:56-64."""
+    image_path = item.get("image_prompt", item.get("image_path", item.get("input_image_path", "")))
+    if image_path and not Path(image_path).exists() and base_dir:
+        image_path = str(Path(base_dir) / image_path)
+    return image_path
+
+
+def first_frame_latent(image_path: str, shape, device, synthetic: bool) -> torch.Tensor:
+    """-> image latents [1, F, 16, h, w]: the encoded first frame followed by F-1 zero frames (App. A.4)."""
+    F_, C, h, w = shape
+    if synthetic:
+        seed = int.from_bytes(hashlib.sha256(Path(image_path).read_bytes()).digest()[:4], "little")
+        first = torch.randn(C, 1, h, w, generator=torch.Generator().manual_seed(seed))
+    else:
+        pre = Path(str(image_path) + ".latent.pt")
+        if not pre.exists():
+            raise RuntimeError(f"{pre} not found: the VAE encoder is not part of this build (SURVEY.md §8 f-4); "
+                               "provide the scaled first-frame latent [16, 1, h, w]")
+        first = torch.load(str(pre), map_location="cpu")
+        if tuple(first.shape) != (C, 1, h, w):
+            raise RuntimeError(f"{pre}: expected shape {(C, 1, h, w)}, got {tuple(first.shape)}")
+    lat = torch.zeros(1, F_, C, h, w, dtype=torch.bfloat16, device=device)
+    lat[0, 0] = first[:, 0].to(device=device, dtype=torch.bfloat16)
+    return lat
+
+
+def build_parser():
+    p = base.build_parser()
+    p.description = "CogVideoX-5B I2V generation"
+    p.set_defaults(base_model="THUDM/CogVideoX-5B-I2V")
+    p.add_argument("--base_dir", type=str, default=None, help="Base dir for relative image paths")
+    return p
+
+
+def generate(args):
+    device = torch.device(f"cuda:{args.gpu_id}")
+    torch.cuda.set_device(device)
+    print(f"Loading base model: {args.base_model}")
+    from ..schedulers import CogVideoXDDIMScheduler
+    if args.synthetic:
+        from ..pipeline import CogVideoXDenoisePipeline
+        from ..transformer import CogVideoXTransformer3D, TransformerConfig
+        from ..vae import AutoencoderKLCogVideoXDecoder, VAEDecoderConfig
+        cfg = TransformerConfig.cogvideox_5b_i2v()
+        cfg.num_layers = args.synthetic
+        cfg.sample_height, cfg.sample_width = args.height // 8, args.width // 8
+        cfg.sample_frames = args.num_frames
+        vae = AutoencoderKLCogVideoXDecoder.random_init(VAEDecoderConfig(), seed=5, device=device)
+        vae.enable_tiling(); vae.enable_slicing()
+        pipe = CogVideoXDenoisePipeline(CogVideoXTransformer3D.random_init(cfg, seed=1234, device=device), CogVideoXDDIMScheduler(), vae=vae,
+                                        vae_scaling_factor=vae.config.scaling_factor)
+        prompts = base._SyntheticPrompts(cfg.text_embed_dim, device)
+    else:
+        pipe, prompts = base.build_pipeline(args, device)
+        pipe.scheduler = CogVideoXDDIMScheduler()                   # the I2V script keeps the checkpoint default (:18-19)
+    if args.lora_path:
+        if not os.path.exists(args.lora_path):
+            print(f"LoRA path not found: {args.lora_path}, using base model")
+        else:
+            from ..lora import merge_lora
+            print(f"Mounting LoRA: {args.lora_path}")
+            merge_lora(pipe.transformer, args.lora_path)
+            print("LoRA merged.")
+    tasks = load_tasks(args.prompt_json, args.num_prompts)
+    if tasks is None:
+        print("Unsupported JSON format")
+        return
+    print(f"Generating {len(tasks)} prompts, seed={args.seed}")
+    output_root = Path(args.output_dir)
+    output_root.mkdir(parents=True, exist_ok=True)
+    negative = prompts("")
+    for idx, (group_id, item) in enumerate(tasks):
+        group_id = str(group_id).replace("/", "_")
+        text_prompt = item.get("text_prompt", item.get("prompt", "")).strip()
+        image_path = resolve_image(item, args.base_dir)
+        if not text_prompt or not image_path:
+            continue
+        if not Path(image_path).exists():
+            print(f"[{idx+1}/{len(tasks)}] Image not found: {image_path}, skipping")
+            continue
+        video_path = output_root / group_id / f"seed_{args.seed}.mp4"
+        video_path.parent.mkdir(parents=True, exist_ok=True)
+        if video_path.exists():
+            print(f"[{idx+1}/{len(tasks)}] Skip existing: {group_id}")
+            continue
+        print(f"[{idx+1}/{len(tasks)}] Generating: {group_id}")
+        try:
+            generator = torch.Generator(device=device).manual_seed(args.seed)
+            _, F_, C, h, w = pipe.latent_shape(1, args.num_frames, args.height, args.width)
+            img_lat = first_frame_latent(image_path, (F_, C, h, w), device, bool(args.synthetic))
+            frames = pipe(prompts(text_prompt), negative, num_frames=args.num_frames, height=args.height, width=args.width,
+                          num_inference_steps=args.num_inference_steps, guidance_scale=args.guidance_scale, generator=generator,
+                          image_latents=img_lat, output_type="pt")
+            base.export_to_video(frames[0], str(video_path), fps=args.fps)
+        except Exception as e:                      # noqa: BLE001
+            print(f"  Failed: {e}")
+        torch.cuda.empty_cache()
+    print("Done.")
+
+
+def main(argv=None):
+    generate(build_parser().parse_args(argv))
+
+
+if __name__ == "__main__":
+    main()
