@@ -297,6 +297,33 @@ def run_ours(args, rank, world, local):
     except Exception as ex:
         vae = {"error": str(ex)}
 
+    # ---- Wan2.2-TI2V-5B guided denoise step (BASELINE.json configs[3] shapes: 81 frames 1280x704, S = 18 480), reported beside
+    wan = None
+    try:
+        from videogpa_b200.wan import WanConfig, WanDenoiseStep, WanTransformer3D, flow_sigmas
+        wm = WanTransformer3D.random_init(WanConfig.ti2v_5b(), seed=21, device=dev)
+        wstep = WanDenoiseStep(wm, guide_scale=5.0)
+        gw = torch.Generator(device=dev).manual_seed(0)
+        wlat = torch.randn(48, 21, 44, 80, device=dev, generator=gw).to(torch.bfloat16)
+        wctx = torch.randn(512, 4096, device=dev, generator=gw).to(torch.bfloat16)
+        wnull = torch.zeros(1, 4096, device=dev, dtype=torch.bfloat16)
+        wS, whw = 21 * 22 * 40, 22 * 40
+        sig = flow_sigmas(50, 5.0)
+        wt = torch.full((1, wS), sig[0] * 1000.0); wt[:, :whw] = 0
+        xw = wstep(wlat, wt, sig[0], sig[1], wctx, wnull, first_frame=wlat[:, :1])
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for i in range(2):
+            xw = wstep(xw, wt, sig[i + 1], sig[i + 2], wctx, wnull, first_frame=wlat[:, :1])
+        w1.record(); torch.cuda.synchronize()
+        wms = w0.elapsed_time(w1) / 2
+        wan = {"metric": "denoised latent tokens/sec Wan2.2-TI2V-5B 81f 1280x704 (cond + uncond forward, CFG, flow Euler)", "value": wS / (wms / 1000.0),
+               "unit": "tokens/s", "ms_per_step": wms, "sequence": wS, "step_tflops": 2 * wm.flops_per_forward(wS) / (wms / 1000.0) / 1e12,
+               "finite": bool(torch.isfinite(xw.float()).all().item()), "weights": "random-init, seed 21"}
+        del wm, wstep, xw
+    except Exception as ex:
+        wan = {"error": str(ex)}
+
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -317,7 +344,7 @@ def run_ours(args, rank, world, local):
                      "flops_per_launch": attn_flops, "avg_launch_ms": attn_avg_ms, "launches_timed": len(attn_ms),
                      "share_of_step": (sum(attn_ms) / ms_max) if ms_max > 0 else None},
         "step_tflops": step_flops * args.steps / (ms_max / 1000.0) / 1e12,
-        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae,
+        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae, "wan_step": wan,
     }
     print(json.dumps(line), flush=True)
 
