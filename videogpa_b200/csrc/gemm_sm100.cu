@@ -10,6 +10,7 @@
 // The two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
 #include "sm100.cuh"
 #include "../../include/videogpa_b200.h"
+#include <stdlib.h>
 
 namespace vgpa {
 
@@ -176,7 +177,11 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
   }
 }
 
-template <int BN, int EPI>
+// CL = 2: the two CTAs of a cluster work on vertically adjacent M tiles of the same N block; each loads only half of the
+// W tile and multicasts it into both CTAs' shared memory, cutting the L2 -> SM operand traffic from 48 KB to 32 KB per
+// k block (ncu showed the MMA warp waiting on TMA data about half of its time with one CTA per tile pair). The stage is
+// released by a multicast tcgen05.commit so that a slot is only refilled once BOTH CTAs have consumed it.
+template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  int M, int N, int K, EpiParams ep) {
@@ -195,17 +200,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BM - 1) / BM;
+  const int cta_rank = (CL == 2) ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int num_m = ((M + BM - 1) / BM + CL - 1) / CL;      // M tiles per CTA of the cluster (pairs for CL = 2)
   const int num_n = N / BN;
   const int num_tiles = num_m * num_n;
   const int nk = (K + BK - 1) / BK;
+  const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], CL);                      // one tcgen05.commit per CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
@@ -219,6 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL == 2) ptx::cluster_sync_all();                        // peer barriers are initialised before anything remote lands
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -228,7 +236,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int first_m = group * GROUP_M;
     const int gsz = min(num_m - first_m, GROUP_M);
     const int in_group = tile - group * per_group;
-    m_blk = first_m + in_group % gsz;
+    m_blk = (first_m + in_group % gsz) * CL + cta_rank;       // may be one past the last M tile: loads are zero-filled, stores masked
     n_blk = in_group / gsz;
   };
 
@@ -237,14 +245,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (ptx::elect_one()) {   // elect.sync keeps TMA / tcgen05 issue free of per-lane waterfall loops
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         for (int kb = 0; kb < nk; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
           ptx::tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          ptx::tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (CL == 2) {
+            ptx::tma_load_2d_multicast(sB + stage * Cfg::B_BYTES + cta_rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * BK,
+                                       n_blk * BN + cta_rank * (BN / 2), 0x3);
+          } else {
+            ptx::tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -256,7 +269,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
@@ -271,7 +284,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // +32 bytes per K=16 step inside the 128B swizzle atom (start-address field is >>4)
             ptx::umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          if (CL == 2) ptx::umma_commit_multicast(&empty_bar[stage], 0x3); else ptx::umma_commit(&empty_bar[stage]);
           if (kb == nk - 1) ptx::umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
@@ -284,7 +297,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int row = m_blk * BM + quarter * 32 + lane;
@@ -330,23 +343,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL == 2) ptx::cluster_sync_all();                        // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CL>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
                 const EpiParams& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    VGPA_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>,
+    VGPA_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, CL>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int num_tiles = ((M + BM - 1) / BM) * (N / BN);
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_bf16_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
-  VGPA_LAUNCH_CHECK("gemm_bf16_kernel");
+  const int num_units = ((((M + BM - 1) / BM) + CL - 1) / CL) * (N / BN);      // tiles (CL = 1) or tile pairs (CL = 2)
+  const int max_units = num_sms() / CL;
+  const int grid = (num_units < max_units ? num_units : max_units) * CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VGPA_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, CL>, tmA, tmB, M, N, K, ep));
   return 0;
 }
 
@@ -366,6 +393,13 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
              "vgpa_linear_bf16: pointers must be 16-byte aligned");
   const int BN = (a->N % 256 == 0) ? 256 : 64;
+  // cluster of 2 with W-tile multicast for the big GEMMs (development knob VGPA_GEMM_CLUSTER=0 turns it off)
+  static int use_cluster = -1;
+  if (use_cluster < 0) {
+    const char* e = getenv("VGPA_GEMM_CLUSTER");
+    use_cluster = e ? atoi(e) : 1;
+  }
+  const int CL = (use_cluster && BN == 256 && (a->M + BM - 1) / BM >= 16) ? 2 : 1;
 
   EpiParams ep;
   memset(&ep, 0, sizeof(ep));
@@ -402,14 +436,15 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
   {
     const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     const uint64_t strides[1] = {(uint64_t)a->K * 2};
-    const uint32_t box[2] = {BK, (uint32_t)BN};
+    const uint32_t box[2] = {BK, (uint32_t)(BN / CL)};
     if (int rc = make_tmap_bf16(&tmB, a->W, 2, dims, strides, box)) return rc;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define VGPA_GEMM_DISPATCH(EPI)                                                          \
   case EPI:                                                                              \
-    return BN == 256 ? launch_gemm<256, EPI>(tmA, tmB, a->M, a->N, a->K, ep, s)          \
-                     : launch_gemm<64, EPI>(tmA, tmB, a->M, a->N, a->K, ep, s);
+    return BN == 256 ? (CL == 2 ? launch_gemm<256, EPI, 2>(tmA, tmB, a->M, a->N, a->K, ep, s)    \
+                                : launch_gemm<256, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s))   \
+                     : launch_gemm<64, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s);
   switch (a->epilogue) {
     VGPA_GEMM_DISPATCH(VGPA_EPI_BIAS)
     VGPA_GEMM_DISPATCH(VGPA_EPI_BIAS_GELU)
