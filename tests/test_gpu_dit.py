@@ -249,3 +249,43 @@ def test_generate_cli_i2v_synthetic(lib, tmp_path, capsys):
     txt = capsys.readouterr().out
     assert "Failed" not in txt and "Image not found" in txt, txt
     assert (out / "s1" / "seed_42.mp4").exists() and not (out / "s2").exists() and not (out / "s3").exists()
+
+
+def test_dpo_shared_step_forward_vs_oracle(lib):
+    """Forward half of `_shared_step` (train/CogVideoX-5B/03_train.py:116-157): noising, policy + reference forwards WITHOUT
+    rotary embeddings, velocity targets and the DPO loss, against the oracle chain on the same timesteps / noise."""
+    from oracle import scorer_np as S
+    from videogpa_b200.train_step import DPOSharedStep
+    from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+    kw = _small_cfg()
+    ocfg = O.DiTConfig(**kw)
+    sd_ref = {k: v.to(BF).float() for k, v in O.random_state_dict(ocfg, seed=7, randomize_norms=True, std=0.05).items()}
+    sd_pol = dict(sd_ref)
+    g = torch.Generator().manual_seed(21)
+    for layer in range(2):                                    # the policy = reference + a (merged) low-rank delta on to_q / to_v
+        for m in ("to_q", "to_v"):
+            k = f"transformer_blocks.{layer}.attn1.{m}.weight"
+            sd_pol[k] = (sd_ref[k] + 0.02 * torch.randn(sd_ref[k].shape[0], 8, generator=g) @ torch.randn(8, sd_ref[k].shape[1], generator=g)).to(BF).float()
+    pol = CogVideoXTransformer3D(TransformerConfig(**kw), sd_pol, device="cuda")
+    ref = CogVideoXTransformer3D(TransformerConfig(**kw), sd_ref, device="cuda")
+    B, C, Fr, H, W, St = 2, 16, 3, 16, 24, 18
+    batch = {"x_win": torch.randn(B, C, Fr, H, W, generator=g), "x_lose": torch.randn(B, C, Fr, H, W, generator=g),
+             "prompt_emb": torch.randn(B, St, 256, generator=g).to(BF)}
+    t = torch.tensor([700, 120])
+    noise = torch.randn(B, Fr, C, H, W, generator=g)
+    step = DPOSharedStep(pol, ref, beta=1.0)
+    out = step.validation_step(batch, timesteps=t.cuda(), noise=noise.cuda())
+    ac = O.cogvideox_alphas_cumprod()
+    xw, xl = batch["x_win"].permute(0, 2, 1, 3, 4), batch["x_lose"].permute(0, 2, 1, 3, 4)
+    fw = lambda sd, x: O.transformer_forward(sd, ocfg, O.add_noise(ac, x, noise, t.numpy()), batch["prompt_emb"].float(), t, None)
+    want = S.dpo_loss(*[a.numpy() for a in (fw(sd_pol, xw), fw(sd_pol, xl), fw(sd_ref, xw), fw(sd_ref, xl),
+                                            O.get_velocity(ac, xw, noise, t.numpy()), O.get_velocity(ac, xl, noise, t.numpy()))], beta=1.0)
+    got = out["loss_output"]
+    # the four MSEs are O(1) and differ between policy and reference only through the low-rank delta: the logit is a small
+    # difference of bf16-accurate numbers, so compare the loss itself loosely and the rewards (MSEs) at bf16 accuracy
+    assert abs(got.winner_reward.item() - want["winner_reward"]) < 2e-2 * abs(want["winner_reward"])
+    assert abs(got.loser_reward.item() - want["loser_reward"]) < 2e-2 * abs(want["loser_reward"])
+    assert abs(got.loss.item() - want["loss"]) < 5e-2
+    assert set(out) == {"val/loss", "val/reward_margin", "val/reward_accuracy", "loss_output"}
+    with pytest.raises(RuntimeError):
+        step.training_step(batch)

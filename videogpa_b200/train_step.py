@@ -1,0 +1,61 @@
+"""Forward half of the DPO `_shared_step` (reference train/CogVideoX-5B/03_train.py:116-157) — what the
+reference's `validation_step` (:189-201) runs under `torch.no_grad()`:
+
+    x_win, x_lose [B, C, F, H, W] -> permute -> [B, F, C, H, W];  t ~ U{0..999};  shared noise
+    x_*_noisy = scheduler.add_noise(x_*, noise, t)
+    v_*_pred = transformer(x_*_noisy, prompt_emb, t)   (policy = base + merged LoRA)   NO image_rotary_emb (the quirk of :134-139)
+    v_*_ref  = ref_transformer(x_*_noisy, prompt_emb, t)
+    v_*_target = scheduler.get_velocity(x_*, noise, t)
+    loss_fn(v_win_pred, v_lose_pred, v_win_ref, v_lose_ref, v_win_target, v_lose_target) -> LossOutput
+
+The winner and the loser share noise, timestep and prompt, so each model sees them as one batch of 2B samples (one pass over
+its weights). The four forwards run on the sm_100a DiT kernels and the loss on the fused DPO kernel. The backward pass
+(attention / GEMM dgrad, LoRA wgrad) is not built: `training_step` raises, `validation_step` is complete.
+"""
+from __future__ import annotations
+
+import torch
+
+from .loss import LossOutput, create_loss_strategy
+from .schedulers import CogVideoXDPMScheduler
+
+
+class DPOSharedStep:
+    def __init__(self, transformer, ref_transformer, beta: float = 1.0, scheduler=None):
+        self.transformer, self.ref_transformer = transformer, ref_transformer
+        self.scheduler = scheduler or CogVideoXDPMScheduler()
+        self.loss_fn = create_loss_strategy(strategy="dpo", beta=beta)
+        self.device = transformer.device
+
+    @torch.no_grad()
+    def _shared_step(self, batch: dict, generator=None, timesteps=None, noise=None) -> LossOutput:
+        dev = self.device
+        x_win = batch["x_win"].to(dev).permute(0, 2, 1, 3, 4).float()            # [B, F, C, H, W]
+        x_lose = batch["x_lose"].to(dev).permute(0, 2, 1, 3, 4).float()
+        prompt_emb = batch["prompt_emb"].to(dev)
+        B = x_win.shape[0]
+        if timesteps is None:
+            timesteps = torch.randint(0, self.scheduler.num_train_timesteps, (B,), device=dev, generator=generator)
+        if noise is None:
+            noise = torch.randn(x_win.shape, device=dev, generator=generator)
+        x_win_noisy = self.scheduler.add_noise(x_win, noise, timesteps)
+        x_lose_noisy = self.scheduler.add_noise(x_lose, noise, timesteps)
+        pair = torch.cat([x_win_noisy, x_lose_noisy], dim=0)                     # one batch of 2B per model
+        emb2 = torch.cat([prompt_emb, prompt_emb], dim=0)
+        t2 = torch.cat([timesteps, timesteps], dim=0)
+        v_pred = self.transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
+        v_ref = self.ref_transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
+        v_win_target = self.scheduler.get_velocity(x_win, noise, timesteps)
+        v_lose_target = self.scheduler.get_velocity(x_lose, noise, timesteps)
+        return self.loss_fn(v_pred[:B].contiguous(), v_pred[B:].contiguous(), v_ref[:B].contiguous(), v_ref[B:].contiguous(),
+                            v_win_target.contiguous(), v_lose_target.contiguous())
+
+    def validation_step(self, batch: dict, batch_idx: int = 0, **kw) -> dict:
+        """-> the scalars the reference logs (:189-201): val/loss, val/reward_margin, val/reward_accuracy."""
+        out = self._shared_step(batch, **kw)
+        return {"val/loss": out.loss, "val/reward_margin": out.reward_margin,
+                "val/reward_accuracy": (out.reward_margin > 0).float().mean(), "loss_output": out}
+
+    def training_step(self, batch: dict, batch_idx: int = 0):
+        raise RuntimeError("the DPO training step needs the DiT backward kernels (attention / GEMM dgrad, LoRA wgrad), which are "
+                           "not built in this round (SURVEY.md §8 f-2); validation_step / _shared_step (forward) are available")
