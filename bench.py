@@ -184,12 +184,30 @@ def run_ours(args, rank, world, local):
 
     import videogpa_b200.transformer as tr_mod
 
+    # the same hook for the GEMM and LayerNorm families (explains the rest of the step)
+    lin_events, ln_events = [], []
+    orig_linear, orig_ln = dense.linear, dense.layernorm_modulate
+
+    def timed(fn, store, flop_fn=None):
+        def f(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            store.append((e0, e1, flop_fn(a, k) if flop_fn else 0.0))
+            return r
+        return f
+
+    timed_linear = timed(orig_linear, lin_events, lambda a, k: 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0])
+    timed_ln = timed(orig_ln, ln_events, lambda a, k: 4.0 * a[0].shape[0] * a[0].shape[1])          # bytes: bf16 read + write
+
     # ---- device-resident throughput
     lat = latents
     with torch.no_grad():
         for i in range(args.warmup):
             lat = pipe.denoise_step(lat, pe, int(timesteps[i % 50]), guidance, rope)
         tr_mod.dense.attention = timed_attention
+        tr_mod.dense.linear, tr_mod.dense.layernorm_modulate = timed_linear, timed_ln
         sampler = ClockSampler(local)
         barrier()
         if rank == 0:
@@ -202,6 +220,7 @@ def run_ours(args, rank, world, local):
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         tr_mod.dense.attention = orig_attention
+        tr_mod.dense.linear, tr_mod.dense.layernorm_modulate = orig_linear, orig_ln
     ms = e0.elapsed_time(e1)
     attn_ms = [a.elapsed_time(b) for a, b in attn_events]
     finite = bool(torch.isfinite(lat.float()).all().item())
@@ -241,6 +260,16 @@ def run_ours(args, rank, world, local):
     attn_avg_ms = sum(attn_ms) / max(1, len(attn_ms))
     attn_tf = attn_flops / (attn_avg_ms / 1000.0) / 1e12
     step_flops = 2 * model.flops_per_sample(S_TEXT, S_VIDEO)
+    lin_ms = sum(a.elapsed_time(b) for a, b, _ in lin_events)
+    lin_fl = sum(f for _, _, f in lin_events)
+    ln_ms = sum(a.elapsed_time(b) for a, b, _ in ln_events)
+    ln_bytes = sum(f for _, _, f in ln_events)
+    families = {
+        "gemm_bf16_kernel": {"launches": len(lin_events), "share_of_step": lin_ms / ms_max if ms_max > 0 else None,
+                             "achieved_tflops": lin_fl / (lin_ms / 1000.0) / 1e12 if lin_ms > 0 else None, "peak_tflops": peak_tf},
+        "ln_modulate_kernel": {"launches": len(ln_events), "share_of_step": ln_ms / ms_max if ms_max > 0 else None,
+                               "achieved_gbs": ln_bytes / (ln_ms / 1000.0) / 1e9 if ln_ms > 0 else None, "peak_gbs": peak_hbm},
+    }
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "attention_traffic.json")) as f:
@@ -343,7 +372,7 @@ def run_ours(args, rank, world, local):
                      "frac": attn_tf / peak_tf, "traffic": traffic, "peak_source": peak_src + " bf16_tflops_sustained",
                      "flops_per_launch": attn_flops, "avg_launch_ms": attn_avg_ms, "launches_timed": len(attn_ms),
                      "share_of_step": (sum(attn_ms) / ms_max) if ms_max > 0 else None},
-        "step_tflops": step_flops * args.steps / (ms_max / 1000.0) / 1e12,
+        "step_tflops": step_flops * args.steps / (ms_max / 1000.0) / 1e12, "kernel_families": families,
         "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae, "wan_step": wan,
     }
     print(json.dumps(line), flush=True)

@@ -4,7 +4,7 @@ import os, sys
 import torch
 import torch.distributed as dist
 sys.path.insert(0, ".")
-from videogpa_b200.parallel import CfgPairGroup, init_from_env
+from videogpa_b200.parallel import CfgPairGroup, CfgPairPeerGroup, gather_frames, init_from_env
 from videogpa_b200.pipeline import CogVideoXDenoisePipeline
 from videogpa_b200.schedulers import CogVideoXDDIMScheduler
 from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
@@ -33,12 +33,26 @@ def run(g, n=3):
     return x, e0.elapsed_time(e1) / n
 x_pair, ms_pair = run(group)
 x_single, ms_single = run(None)
+peer_ok, ms_peer, same_peer = True, float("nan"), False
+try:
+    peer = CfgPairPeerGroup(rank, world)
+    x_peer, ms_peer = run(peer)
+    same_peer = bool(torch.equal(x_peer, x_single))
+except Exception as ex:                                   # noqa: BLE001
+    peer_ok = False
+    if rank == 0:
+        print("peer-memory exchange unavailable:", ex)
+frames = torch.full((1 + rank, 4, 8, 3), rank, dtype=torch.uint8, device=dev)
+got = gather_frames(frames, rank, world)
+gather_ok = rank != 0 or (len(got) == world and all(int(g.shape[0]) == 1 + r and bool((g == r).all()) for r, g in enumerate(got)))
 same = bool(torch.equal(x_pair, x_single))
 both = [torch.empty_like(x_pair) for _ in range(world)]
 dist.all_gather(both, x_pair)
 ident = bool(torch.equal(both[0], both[1]))
-t = torch.tensor([ms_pair, ms_single], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+t = torch.tensor([ms_pair, ms_single, ms_peer if peer_ok else 0.0], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(f"CFG-pair shard over 2 GPUs ({layers} layers): {t[0].item():.1f} ms/step vs {t[1].item():.1f} ms/step batched on one GPU "
           f"(speed-up {t[1].item()/t[0].item():.2f}x); latents identical across the pair: {ident}; identical to the single-GPU batched step: {same}")
+    print(f"peer-memory fused exchange (no NCCL on the data path): {t[2].item():.1f} ms/step, identical to the single-GPU step: {same_peer}; "
+          f"final frame gather over NCCL ok: {gather_ok}")
 dist.destroy_process_group()

@@ -66,6 +66,46 @@ class CfgPairGroup:
         return both[0], both[1]
 
 
+class CfgPairPeerGroup(CfgPairGroup):
+    """CFG-pair sharding with the exchange FUSED into the guidance + scheduler kernel over NVLink peer memory.
+
+    Instead of an NCCL all-gather followed by the update kernel, every rank publishes its noise prediction in a symmetric
+    (peer-mapped) buffer, and `vgpa_cfg_scheduler_step` reads the partner's half straight through the peer pointer while it
+    combines guidance and applies the scheduler update: one kernel does the transfer and the math. Two device-side barriers
+    on the symmetric-memory signal pads order "partner has written" before and "partner has read" after the kernel; no
+    collective library call is on the data path. Falls back to nothing: construction raises if peer access is unavailable.
+    """
+
+    def __init__(self, rank: int, world: int):
+        super().__init__(rank, world)
+        self._buf = None
+        self._hdl = None
+        self._n = 0
+
+    def _ensure(self, pred: torch.Tensor):
+        if self._buf is not None and self._n == pred.numel():
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+        self._buf = symm_mem.empty(pred.numel(), dtype=pred.dtype, device=pred.device)
+        self._hdl = symm_mem.rendezvous(self._buf, self.group)
+        self._n = pred.numel()
+        if self._hdl.world_size != 2:
+            raise RuntimeError("CFG-pair peer exchange needs a 2-rank group")
+
+    def peer_views(self, pred: torch.Tensor):
+        """Publish `pred` and return (pred_uncond, pred_cond) where the partner's half is a tensor aliasing ITS memory."""
+        self._ensure(pred)
+        self._buf.copy_(pred.reshape(-1))
+        self._hdl.barrier(channel=0)                                   # both halves are written
+        me = self._hdl.rank
+        mine = self._buf.view(pred.shape)
+        theirs = self._hdl.get_buffer(1 - me, tuple(pred.shape), pred.dtype)
+        return (mine, theirs) if self.branch == 0 else (theirs, mine)
+
+    def release(self):
+        self._hdl.barrier(channel=1)                                   # the partner has finished reading my half
+
+
 def gather_frames(frames: torch.Tensor, rank: int, world: int, dst: int = 0):
     """Final decoded-frame gather: every rank contributes a [n_i, ...] uint8 tensor with identical trailing
     shape; rank `dst` receives the list ordered by rank, the others get None."""

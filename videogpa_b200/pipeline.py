@@ -79,6 +79,12 @@ class CogVideoXDenoisePipeline:
             ts = torch.full((B,), float(t), device=self.device, dtype=torch.float32)
             pred = self.transformer(hidden_states=x, encoder_hidden_states=mine, timestep=ts, image_rotary_emb=rope,
                                     return_dict=False)[0]
+            if hasattr(cfg_group, "peer_views"):
+                # exchange fused into the guidance + scheduler kernel: the partner's prediction is read over NVLink peer memory
+                pred_uncond, pred_cond = cfg_group.peer_views(pred.contiguous())
+                nxt = self.scheduler.step_cfg(pred_cond, pred_uncond, int(t), latents, guidance_scale, generator=generator, out=out)
+                cfg_group.release()
+                return nxt
             pred_uncond, pred_cond = cfg_group.exchange(pred)
         return self.scheduler.step_cfg(pred_cond.contiguous(), pred_uncond.contiguous(), int(t), latents, guidance_scale,
                                        generator=generator, out=out)
