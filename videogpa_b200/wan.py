@@ -333,15 +333,22 @@ class WanDenoiseStep:
     @torch.no_grad()
     def __call__(self, latent, t_tokens, sigma: float, sigma_next: float, context, context_null, cfg_group=None, first_frame=None):
         lat = latent.to(device=self.model.device, dtype=BF16).contiguous()
+        peer = False
         if cfg_group is None:
             cond = self.model([lat], t_tokens, [context])[0]
             uncond = self.model([lat], t_tokens, [context_null])[0]
         else:
             mine = self.model([lat], t_tokens, [context if cfg_group.branch == 1 else context_null])[0]
-            uncond, cond = cfg_group.exchange(mine)
+            if hasattr(cfg_group, "peer_views"):               # partner's prediction read over NVLink peer memory by the kernel below
+                uncond, cond = cfg_group.peer_views(mine.contiguous())
+                peer = True
+            else:
+                uncond, cond = cfg_group.exchange(mine)
         # x_next = x + (sigma_next - sigma) * v   <=>   x0 := v (sqrt_alpha_t = 0, sqrt_beta_t = -1), prev = 1 * x + dsigma * x0
         nxt = dense.cfg_scheduler_step(cond.contiguous(), uncond.contiguous(), lat, mode=dense.SCHED_DDIM, guidance=self.guide_scale,
                                        sqrt_alpha_t=0.0, sqrt_beta_t=-1.0, c_sample=1.0, c_x0=float(sigma_next - sigma))
+        if peer:
+            cfg_group.release()
         if first_frame is not None:                                     # TI2V: the first latent frame stays the encoded image
             nxt[:, :1].copy_(first_frame.to(nxt.dtype))
         return nxt
