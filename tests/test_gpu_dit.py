@@ -36,7 +36,7 @@ def test_gemm_bias(lib, M, N, K):
 
 
 @pytest.mark.parametrize("B,H,S,Skv", [(1, 1, 128, 128), (1, 2, 300, 300), (2, 3, 1000, 1000), (1, 2, 300, 517), (1, 2, 4096, 4096),
-                                       (1, 1, 17776, 17776)])
+                                       (1, 1, 17776, 17776), (1, 1, 1, 1), (2, 2, 5, 70), (1, 1, 257, 129), (1, 3, 130, 64)])
 def test_attention(lib, B, H, S, Skv):
     from videogpa_b200 import dense
     torch.manual_seed(S)
@@ -50,6 +50,23 @@ def test_attention(lib, B, H, S, Skv):
     ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, S, D)
     assert torch.isfinite(out.float()).all()
     assert relerr(out, ref) < 1e-2                                   # P is rounded to bf16 before PV, output to bf16
+
+
+def test_attention_four_warpgroup_variant_matches(lib):
+    """The alternative head_dim-64 kernel (attention_d64x4_sm100.cu, VGPA_ATTN_X4=1) is selected per process through an
+    environment knob: run it in a subprocess and compare with torch SDPA on the same seeded inputs."""
+    import os, subprocess, sys
+    code = ("import torch, torch.nn.functional as F, sys; sys.path.insert(0, '.'); from videogpa_b200 import dense; torch.manual_seed(0);"
+            "q=torch.randn(2,700,128,device='cuda').bfloat16(); kv=torch.randn(2,517,256,device='cuda').bfloat16();"
+            "o=dense.attention(q,kv[...,:128],kv[...,128:],2);"
+            "sp=lambda t,n: t.reshape(2,n,2,64).transpose(1,2).float();"
+            "r=F.scaled_dot_product_attention(sp(q,700),sp(kv[...,:128],517),sp(kv[...,128:],517)).transpose(1,2).reshape(2,700,128);"
+            "print('ERR', ((o.float()-r).abs().max()/r.abs().max()).item())")
+    env = dict(os.environ, VGPA_ATTN_X4="1", VGPA_ATTN_NPOLY="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert float(out.stdout.split("ERR")[1]) < 1e-2
 
 
 def test_attention_peaked_rows_rescale_path(lib):
