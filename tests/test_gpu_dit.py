@@ -306,3 +306,24 @@ def test_dpo_shared_step_forward_vs_oracle(lib):
     assert set(out) == {"val/loss", "val/reward_margin", "val/reward_accuracy", "loss_output"}
     with pytest.raises(RuntimeError):
         step.training_step(batch)
+
+
+def test_full_size_block_vs_oracle(lib):
+    """BASELINE.json configs[1] at its real size: one CogVideoXBlock-deep forward at S = 226 + 17 550 tokens, D = 3072, 48 heads,
+    with 3-D RoPE, against the fp32 CPU oracle on the same bf16-rounded weights (about 15 s of CPU work)."""
+    from videogpa_b200.rope import get_3d_rotary_pos_embed
+    from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+    ocfg = O.DiTConfig(num_layers=1)
+    sd = {k: v.to(BF).float() for k, v in O.random_state_dict(ocfg, seed=1234, std=0.02).items()}
+    cfg = TransformerConfig.cogvideox_5b(); cfg.num_layers = 1
+    model = CogVideoXTransformer3D(cfg, sd, device="cuda")
+    g = torch.Generator().manual_seed(42)
+    hs = torch.randn(1, 13, 16, 60, 90, generator=g).to(BF)
+    enc = torch.randn(1, 226, 4096, generator=g).to(BF)
+    t = torch.tensor([999])
+    rope = get_3d_rotary_pos_embed(64, 30, 45, 13)
+    out = model(hidden_states=hs.cuda(), encoder_hidden_states=enc.cuda(), timestep=t.cuda(), image_rotary_emb=rope, return_dict=False)[0].cpu()
+    torch.set_num_threads(max(1, (os.cpu_count() or 1)))
+    ref = O.transformer_forward(sd, ocfg, hs.float(), enc.float(), t, O.rope_3d(ocfg, 13, 60, 90))
+    assert out.shape == ref.shape == (1, 13, 16, 60, 90)
+    assert relerr(out, ref) < 2e-2, relerr(out, ref)
