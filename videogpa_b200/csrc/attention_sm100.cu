@@ -5,28 +5,33 @@
 // train/CogVideoX-5B/03_train.py:134-151). q/k arrive already LayerNorm'ed and rotated by the
 // fused QKV GEMM epilogue (gemm_sm100.cu), so this kernel is softmax(q k^T / sqrt(d)) v only.
 //
-// One CTA = 256 query rows of one (batch, head): two 128-row Q tiles that ping-pong on the tensor
-// pipe. 384 threads:
-//   warpgroup 0: warp 0 = TMA producer (Q once, then K_j / V_j tiles through a 6-slot ring),
-//                warp 1 = tcgen05 issuer (S_t = Q_t K_j^T and O_t += P_t V_j, all in TMEM),
+// One CTA = 256 query rows of one (batch, head): two 128-row Q tiles. 384 threads:
+//   warpgroup 0: warp 0 = TMA producer (Q once, then K / V tiles through a 6-slot ring of 16 KB tiles),
+//                warp 1 = tcgen05 issuer under elect.sync (S_t = Q_t K_j^T, O_t += P_t V_j, all in TMEM),
 //                warps 2-3 idle (they only donate registers)
-//   warpgroup 1: softmax of Q tile 0 (one thread = one query row, straight out of TMEM lanes)
+//   warpgroup 1: softmax of Q tile 0 (one thread = one query row, straight out of its TMEM lane)
 //   warpgroup 2: softmax of Q tile 1
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).
-// P_t is written by the softmax threads as bf16 into 128B-swizzled smem and consumed as the A
-// operand of the PV MMA. The row max used for the exponentials is allowed to go stale by up to
-// 2^8 (O/l are rescaled only when a row max grows by more than that), which keeps the TMEM
-// read-modify-write of O off the steady-state path; the final O/l is exact.
+// TMEM columns (all 512 used): S_t [t*128, +128) fp32;  P_t half hh [256 + t*64 + hh*32, +32) bf16 pairs;
+// O_t [384 + t*64, +64) fp32. P never touches shared memory: the softmax threads store it back to TMEM
+// (tcgen05.st) and the PV product is a TS-form tcgen05.mma (A operand from TMEM), which halves the shared-memory
+// traffic of the kernel.
 //
-// With head_dim 64 there are only 128 MMA FLOPs per softmax element, so the softmax warpgroups (MUFU
-// ex2 at 16/clk/SM, FMA/ALU issue) are the bound, not the tensor pipe. The kernel is therefore built
-// to keep them busy:
-//   * a softmax thread pulls its whole S row (128 fp32) into registers and releases the TMEM S tile
-//     at once (s_free), so S_t(j+1) = Q_t K_{j+1}^T is computed while softmax(j) is still running;
-//   * scale/subtract, row-sum and (part of) the exponentials run as packed f32x2 FMA-pipe ops; NPOLY of
-//     the 64 column pairs of a row use a Cody-Waite + degree-3 polynomial exp2 on the FMA pipe instead
-//     of MUFU (relative error ~1e-4, below the bf16 rounding of P), balancing the two pipes;
-//   * the row max uses 3-input FMNMX3.
+// With head_dim 64 there are only 128 MMA FLOPs per softmax element, so the softmax warpgroups (MUFU ex2 at
+// 16/clk/SM, FMA/ALU issue) are the bound, not the tensor pipe. The kernel is built to keep them busy:
+//   * split-half software pipelining: a thread holds the row as two 64-column register halves; while it works on
+//     one half the other half of this tile / the first half of the next tile streams in from TMEM, and the S tile
+//     is released (s_free) as soon as the row is in registers, so S_t(j+1) is computed under softmax(j);
+//   * P is published per half (p_ready[t][hh]) and the wait::st + arrive is deferred into the next half's
+//     instruction stream; PV runs per half (K = 64);
+//   * lazy rescale: the exponent offset may go stale by up to 2^8 (O / l are rescaled only when a half-row max
+//     grows by more than that), which keeps the TMEM read-modify-write of O off the steady-state path; the final
+//     O / l is exact;
+//   * scale/subtract, row-sum and (part of) the exponentials run as packed f32x2 FMA-pipe ops; NPOLY of the 64
+//     column pairs of a row use a Cody-Waite + degree-3 polynomial exp2 on the FMA pipe instead of MUFU (relative
+//     error ~1e-4, below the bf16 rounding of P); the row max uses 3-input FMNMX3;
+//   * the issuer walks the events of the two Q tiles in an order that keeps warpgroup 2 about half a tile behind
+//     warpgroup 1, so the MUFU-idle windows of the two warps sharing a scheduler do not coincide.
+// Measurements and the design history: profiles/r01_attn_ncu_summary.md.
 #include "sm100.cuh"
 #include "attn_common.cuh"
 #include "../../include/videogpa_b200.h"
