@@ -1,0 +1,76 @@
+"""CPU: host-side logic of the VAE decoder and Wan mirrors against the oracles / torch (no GPU, no kernels)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vae_torch as V
+from oracle import wan_torch as OW
+
+
+def test_vae_frame_batches_and_time_maps_match_torch_interpolate():
+    from videogpa_b200.vae import AutoencoderKLCogVideoXDecoder as D
+    for n in (1, 2, 3, 5, 13, 21):
+        assert D.frame_batches(n, 2) == V.frame_batches(n, 2)
+    assert D.frame_batches(13, 2) == [(0, 3), (3, 5), (5, 7), (7, 9), (9, 11), (11, 13)]
+    # SpatialNorm3D resizes zq with nearest interpolation, the first frame separately when T > 1 is odd (App. A.5)
+    for T, Tz in [(1, 1), (2, 2), (3, 3), (4, 2), (5, 3), (8, 2), (9, 3), (2, 1), (4, 1), (16, 2)]:
+        idx = torch.arange(Tz, dtype=torch.float32).view(1, 1, Tz, 1, 1)
+        if T > 1 and T % 2 == 1:
+            ref = torch.cat([F.interpolate(idx[:, :, :1], size=(1, 1, 1)), F.interpolate(idx[:, :, 1:], size=(T - 1, 1, 1))], dim=2) \
+                if Tz > 1 else torch.zeros(1, 1, T, 1, 1)
+        else:
+            ref = F.interpolate(idx, size=(T, 1, 1))
+        assert D._tz_map(T, Tz) == [int(v) for v in ref.flatten().tolist()], (T, Tz)
+
+
+def test_vae_tiling_geometry_matches_oracle_and_survey():
+    from videogpa_b200.vae import VAEDecoderConfig
+    geo = V.tiling_geometry(V.VAEConfig())
+    assert geo == dict(tile_latent_h=30, tile_latent_w=45, overlap_h=25, overlap_w=36, blend_h=40, blend_w=72, limit_h=200, limit_w=288)
+    c = VAEDecoderConfig()
+    assert (c.sample_height // 2 // 8, c.sample_width // 2 // 8) == (30, 45)
+    assert int(30 * (1 - c.tile_overlap_factor_height)) == 25 and int(45 * (1 - c.tile_overlap_factor_width)) == 36
+    assert list(range(0, 60, 25)) == [0, 25, 50] and list(range(0, 90, 36)) == [0, 36, 72]          # the 3 x 3 tiles of 60 x 90 latents
+
+
+def test_wan_rope_sigmas_and_timestep_rules_match_oracle():
+    from videogpa_b200.wan import WanConfig, WanTransformer3D, flow_sigmas, rope_tables
+    for (dim, heads, f, h, w) in [(3072, 24, 3, 4, 5), (256, 2, 2, 3, 3)]:
+        cos, sin = rope_tables(WanConfig(dim=dim, num_heads=heads), f, h, w)
+        oc, os_ = OW.rope_tables(OW.WanConfig(dim=dim, num_heads=heads), f, h, w)
+        assert torch.equal(cos, oc) and torch.equal(sin, os_)
+        assert cos.shape == (f * h * w, 128)
+    d = 128
+    assert [d - 4 * (d // 6), 2 * (d // 6), 2 * (d // 6)] == [44, 42, 42]                             # App. A.7 split
+    s, so = flow_sigmas(50, 5.0), OW.flow_sigmas(50, 5.0)
+    assert len(s) == 51 and max(abs(a - float(b)) for a, b in zip(s, so)) < 1e-12
+    two = WanTransformer3D._two_timesteps
+    assert two(torch.tensor(500.0), 10, 4) == (500.0, 500.0)
+    t = torch.full((10,), 900.0); t[:4] = 0
+    assert two(t, 10, 4) == (0.0, 900.0)
+    with pytest.raises(RuntimeError):
+        two(torch.arange(10.0), 10, 4)
+    with pytest.raises(RuntimeError):
+        two(torch.zeros(7), 10, 4)
+
+
+def test_c_abi_argument_validation_of_new_entry_points(lib):
+    """Validation happens before any CUDA call, so it is checkable without a GPU."""
+    import ctypes as C
+    from videogpa_b200 import _lib
+    assert lib.vgpa_conv3d_causal_bf16(None, None) != 0 and b"null args" in lib.vgpa_last_error()
+    a = _lib.Conv3dArgs()
+    a.x = a.w = a.out = 0x1000
+    a.T, a.H, a.W, a.Cin, a.Cout, a.Cout_pad, a.KT, a.ldo = 1, 8, 8, 48, 64, 64, 3, 64
+    assert lib.vgpa_conv3d_causal_bf16(C.byref(a), None) != 0 and b"multiple of 64" in lib.vgpa_last_error()
+    a.Cin, a.KT = 64, 2
+    assert lib.vgpa_conv3d_causal_bf16(C.byref(a), None) != 0 and b"KT must be 1 or 3" in lib.vgpa_last_error()
+    assert lib.vgpa_groupnorm_workspace_bytes(512) == 592 * 2 * 512 * 4
+    assert lib.vgpa_groupnorm_stats_bf16(None, 10, 64, 32, 1e-6, None, 0, None, None) != 0
+    assert lib.vgpa_spatialnorm_apply_bf16(None, None) != 0 and lib.vgpa_vae_compose_tiles_bf16(None, None) != 0
+    assert lib.vgpa_rmsnorm_rope_bf16(None, 1, 256, 256, None, 1e-6, None, None, 128, 0, None) != 0
+    assert lib.vgpa_add_rows_bf16(None, None, None, 1, 8, 8, None) != 0
+    at = _lib.AttentionArgs()
+    at.q = at.k = at.v = at.out = 0x1000
+    at.B, at.H, at.Sq, at.Skv, at.head_dim = 1, 1, 8, 8, 96
+    assert lib.vgpa_attention_bf16(C.byref(at), None) != 0 and b"head_dim must be 64 or 128" in lib.vgpa_last_error()
