@@ -10,6 +10,8 @@ sd = V.random_state_dict(cfg, seed=5, dtype=torch.bfloat16)
 dec = AutoencoderKLCogVideoXDecoder(sd, VAEDecoderConfig(), device="cuda")
 dec.enable_tiling(); dec.enable_slicing()
 z = torch.randn(1, 16, 13, 60, 90, device="cuda").to(torch.bfloat16)
+import os
+dec.tile_streams = int(os.environ.get("VAE_STREAMS", "4"))
 for it in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

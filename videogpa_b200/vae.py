@@ -70,6 +70,8 @@ class AutoencoderKLCogVideoXDecoder:
         self.dtype = BF16
         self.use_tiling = False
         self.use_slicing = False
+        self.tile_streams = 4           # latent tiles are independent: decode them on this many CUDA streams side by side
+        self._streams = None
         c = self.config
         self.rc = tuple(reversed(c.block_out_channels))
         self.temporal_compress_level = int(math.log2(c.temporal_compression_ratio))
@@ -238,12 +240,16 @@ class AutoencoderKLCogVideoXDecoder:
     def _gn_stats(self, x: torch.Tensor, C_: int) -> torch.Tensor:
         lib = _lib.load()
         need = lib.vgpa_groupnorm_workspace_bytes(C_)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=self.device)
+        if self._ws is None:
+            self._ws = {}
+        key = torch.cuda.current_stream().cuda_stream            # one scratch buffer per stream: tiles decode concurrently
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._ws[key] = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=self.device)
         out = torch.empty(2 * self.config.norm_num_groups, dtype=torch.float32, device=self.device)
         n_pix = x.numel() // C_
-        _lib.check(lib.vgpa_groupnorm_stats_bf16(x.data_ptr(), n_pix, C_, self.config.norm_num_groups, 1e-6, self._ws.data_ptr(),
-                                                 self._ws.numel(), out.data_ptr(), _lib.current_stream()), "vgpa_groupnorm_stats_bf16")
+        _lib.check(lib.vgpa_groupnorm_stats_bf16(x.data_ptr(), n_pix, C_, self.config.norm_num_groups, 1e-6, ws.data_ptr(),
+                                                 ws.numel(), out.data_ptr(), _lib.current_stream()), "vgpa_groupnorm_stats_bf16")
         return out
 
     @staticmethod
@@ -419,9 +425,26 @@ class AutoencoderKLCogVideoXDecoder:
         samples = []
         for b in range(B):
             tiles = []
-            for y0 in ys:
-                for x0 in xs:
+            origins = [(y0, x0) for y0 in ys for x0 in xs]
+            n_str = max(1, min(self.tile_streams, len(origins)))
+            if n_str == 1:
+                for (y0, x0) in origins:
                     tiles.append(self._decode_tile(zcl[b, :, y0:y0 + tlh, x0:x0 + tlw].contiguous()))
+            else:
+                # the low-resolution layers of one 30x45 tile fill only a fraction of the 148 SMs; independent tiles on
+                # separate streams overlap them (results are unchanged: every tile's kernels run in order on its stream)
+                if self._streams is None or len(self._streams) < n_str:
+                    self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n_str)]
+                cur = torch.cuda.current_stream()
+                for k, (y0, x0) in enumerate(origins):
+                    st = self._streams[k % n_str]
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        tiles.append(self._decode_tile(zcl[b, :, y0:y0 + tlh, x0:x0 + tlw].contiguous()))
+                for st in self._streams[:n_str]:
+                    cur.wait_stream(st)
+                for t in tiles:
+                    t.record_stream(cur)
             To = tiles[0].shape[0]
             out = torch.empty((3, To, H * s8, W * s8), dtype=BF16, device=self.device)
             a = ComposeArgs()
