@@ -29,9 +29,9 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, long long n_pixels, int C
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   if (pslot < pix_per_iter) {
-    for (long long pix = static_cast<long long>(blockIdx.x) * pix_per_iter + pslot; pix < n_pixels;
-         pix += static_cast<long long>(gridDim.x) * pix_per_iter) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + pix * C + v * 8);
+    const long long stride = static_cast<long long>(gridDim.x) * pix_per_iter;
+    const __nv_bfloat16* xv = x + v * 8;
+    auto fold = [&](const uint4& u) {
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -39,7 +39,17 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, long long n_pixels, int C
         s[2 * i] += f.x; q[2 * i] += f.x * f.x;
         s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
       }
+    };
+    long long pix = static_cast<long long>(blockIdx.x) * pix_per_iter + pslot;
+    // four independent 16-byte loads in flight per thread; the fold order (increasing pixel) is unchanged
+    for (; pix + 3 * stride < n_pixels; pix += 4 * stride) {
+      const uint4 u0 = *reinterpret_cast<const uint4*>(xv + pix * C);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(xv + (pix + stride) * C);
+      const uint4 u2 = *reinterpret_cast<const uint4*>(xv + (pix + 2 * stride) * C);
+      const uint4 u3 = *reinterpret_cast<const uint4*>(xv + (pix + 3 * stride) * C);
+      fold(u0); fold(u1); fold(u2); fold(u3);
     }
+    for (; pix < n_pixels; pix += stride) fold(*reinterpret_cast<const uint4*>(xv + pix * C));
   }
   for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sh[i] = 0.f;
   __syncthreads();
@@ -96,49 +106,86 @@ struct SnParams {
   int tz_of_t[16];
 };
 
-__global__ void __launch_bounds__(256)
+// Thread mapping shared by the apply / upsample kernels: a block walks rows (t, h) of the [T, H, W, C] tensor; thread
+// `tid` owns the 8 channels v = tid % (C/8) of pixels slot, slot + 256/(C/8), ... of the row, so everything that depends
+// on the channel (GroupNorm scale/shift) is loop-invariant and no per-element integer division is left in the loop.
+// blockIdx.y splits long rows when there are too few of them to fill the SMs.
+__global__ void __launch_bounds__(256, 4)
 spatialnorm_apply_kernel(SnParams p) {
-  const int vec_per_pixel = p.C / 8;
-  const long long n_vec = static_cast<long long>(p.T) * p.H * p.W * vec_per_pixel;
-  const int cpg = p.C / p.groups;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % vec_per_pixel);
-    const long long pix = i / vec_per_pixel;
-    const int w = static_cast<int>(pix % p.W);
-    const long long th = pix / p.W;
-    const int h = static_cast<int>(th % p.H);
-    const int t = static_cast<int>(th / p.H);
-    const long long zpix = (static_cast<long long>(p.tz_of_t[t]) * p.Hz + (h >> p.shift)) * p.Wz + (w >> p.shift);
-    const int c0 = v * 8;
-    const uint4 xu = *reinterpret_cast<const uint4*>(p.x + pix * p.C + c0);
+  const int C = p.C, vpp = C >> 3, ppi = 256 / vpp;
+  const int v = threadIdx.x % vpp, slot = threadIdx.x / vpp;
+  if (slot >= ppi) return;
+  const int c0 = v * 8, cpg = C / p.groups;
+  // y = a*x + b with a = rstd*gamma, b = beta - mean*a (the form torch's own GroupNorm kernel evaluates)
+  float a[8], b[8];
+  {
     const uint4 gu = __ldg(reinterpret_cast<const uint4*>(p.gamma + c0));
     const uint4 bu = __ldg(reinterpret_cast<const uint4*>(p.beta + c0));
-    const uint4 yu = __ldg(reinterpret_cast<const uint4*>(p.y_lat + zpix * p.ld_lat + c0));
-    const uint4 zu = __ldg(reinterpret_cast<const uint4*>(p.b_lat + zpix * p.ld_lat + c0));
-    const uint32_t xa[4] = {xu.x, xu.y, xu.z, xu.w}, ga[4] = {gu.x, gu.y, gu.z, gu.w}, ba[4] = {bu.x, bu.y, bu.z, bu.w},
-                   ya[4] = {yu.x, yu.y, yu.z, yu.w}, za[4] = {zu.x, zu.y, zu.z, zu.w};
-    uint32_t o[4];
+    const uint32_t ga[4] = {gu.x, gu.y, gu.z, gu.w}, ba[4] = {bu.x, bu.y, bu.z, bu.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 xf = unpack_bf16x2(xa[k]), gf = unpack_bf16x2(ga[k]), bf = unpack_bf16x2(ba[k]),
-                   yf = unpack_bf16x2(ya[k]), zf = unpack_bf16x2(za[k]);
-      float r[2];
-      const float xs[2] = {xf.x, xf.y}, gs[2] = {gf.x, gf.y}, bs[2] = {bf.x, bf.y}, ys[2] = {yf.x, yf.y}, zs[2] = {zf.x, zf.y};
+      const float2 gf = unpack_bf16x2(ga[k]), bf = unpack_bf16x2(ba[k]);
+      const float gs[2] = {gf.x, gf.y}, bs[2] = {bf.x, bf.y};
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int g = (c0 + 2 * k + e) / cpg;
         const float mean = __ldg(p.mean_rstd + g), rstd = __ldg(p.mean_rstd + p.groups + g);
-        // roundings where eager bf16 has them: GroupNorm output, * conv_y, + conv_b, SiLU
-        float n = bf16_round((xs[e] - mean) * rstd * gs[e] + bs[e]);
-        n = bf16_round(bf16_round(n * ys[e]) + zs[e]);
-        if (p.silu) n = n / (1.0f + __expf(-n));
-        r[e] = n;
+        a[2 * k + e] = rstd * gs[e];
+        b[2 * k + e] = fmaf(-mean, a[2 * k + e], bs[e]);
       }
-      o[k] = pack_bf16x2(r[0], r[1]);
     }
-    *reinterpret_cast<uint4*>(p.out + pix * p.C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
   }
+  const int w_chunk = (p.W + gridDim.y - 1) / gridDim.y;
+  const int w_begin = blockIdx.y * w_chunk, w_end = min(p.W, w_begin + w_chunk);
+  const int rows = p.T * p.H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int t = row / p.H, h = row - t * p.H;
+    const long long zrow = (static_cast<long long>(p.tz_of_t[t]) * p.Hz + (h >> p.shift)) * p.Wz;
+    const __nv_bfloat16* xrow = p.x + static_cast<long long>(row) * p.W * C + c0;
+    __nv_bfloat16* orow = p.out + static_cast<long long>(row) * p.W * C + c0;
+    const __nv_bfloat16* yrow = p.y_lat + zrow * p.ld_lat + c0;
+    const __nv_bfloat16* brow = p.b_lat + zrow * p.ld_lat + c0;
+#pragma unroll 2
+    for (int w = w_begin + slot; w < w_end; w += ppi) {
+      const long long zoff = static_cast<long long>(w >> p.shift) * p.ld_lat;
+      const uint4 xu = *reinterpret_cast<const uint4*>(xrow + static_cast<long long>(w) * C);
+      const uint4 yu = __ldg(reinterpret_cast<const uint4*>(yrow + zoff));
+      const uint4 zu = __ldg(reinterpret_cast<const uint4*>(brow + zoff));
+      const uint32_t xa[4] = {xu.x, xu.y, xu.z, xu.w}, ya[4] = {yu.x, yu.y, yu.z, yu.w}, za[4] = {zu.x, zu.y, zu.z, zu.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // roundings where eager bf16 has them: GroupNorm output, * conv_y, + conv_b, SiLU (packed bf16x2 mul / add
+        // with explicit .rn so they are not contracted into one fma)
+        const float2 xf = unpack_bf16x2(xa[k]);
+        const uint32_t n1 = pack_bf16x2(fmaf(xf.x, a[2 * k], b[2 * k]), fmaf(xf.y, a[2 * k + 1], b[2 * k + 1]));
+        __nv_bfloat162 n = *reinterpret_cast<const __nv_bfloat162*>(&n1);
+        n = __hmul2_rn(n, *reinterpret_cast<const __nv_bfloat162*>(&ya[k]));
+        n = __hadd2_rn(n, *reinterpret_cast<const __nv_bfloat162*>(&za[k]));
+        uint32_t r = *reinterpret_cast<const uint32_t*>(&n);
+        if (p.silu) {
+          const float2 f = unpack_bf16x2(r);
+          r = pack_bf16x2(__fdividef(f.x, 1.0f + __expf(-f.x)), __fdividef(f.y, 1.0f + __expf(-f.y)));
+        }
+        o[k] = r;
+      }
+      *reinterpret_cast<uint4*>(orow + static_cast<long long>(w) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// grid for the row-walking kernels: one block per row up to 148 x 8 blocks; rows are split along W when few
+inline dim3 row_grid(int rows, int W, int ppi) {
+  const int target = 148 * 4;
+  int gx = rows < 148 * 8 ? rows : 148 * 8;
+  int gy = 1;
+  if (rows < target) {
+    gy = (target + rows - 1) / rows;
+    const int max_split = (W + ppi - 1) / ppi;         // at least one loop trip per block
+    if (gy > max_split) gy = max_split;
+    if (gy < 1) gy = 1;
+  }
+  return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy), 1);
 }
 
 // ---------------------------------------------------------------------------------------------- nearest upsample x2
@@ -151,19 +198,21 @@ struct UpParams {
 
 __global__ void __launch_bounds__(256)
 upsample_nearest_kernel(UpParams p) {
-  const int vec_per_pixel = p.C / 8;
+  const int C = p.C, vpp = C >> 3, ppi = 256 / vpp;
+  const int v = threadIdx.x % vpp, slot = threadIdx.x / vpp;
+  if (slot >= ppi) return;
   const int Ho = 2 * p.H, Wo = 2 * p.W;
-  const long long n_vec = static_cast<long long>(p.T_out) * Ho * Wo * vec_per_pixel;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % vec_per_pixel);
-    const long long pix = i / vec_per_pixel;
-    const int w = static_cast<int>(pix % Wo);
-    const long long th = pix / Wo;
-    const int h = static_cast<int>(th % Ho);
-    const int t = static_cast<int>(th / Ho);
-    const long long src = (static_cast<long long>(p.t_src[t]) * p.H + (h >> 1)) * p.W + (w >> 1);
-    reinterpret_cast<uint4*>(p.out)[i] = __ldg(reinterpret_cast<const uint4*>(p.x + src * p.C) + v);
+  const int w_chunk = (Wo + gridDim.y - 1) / gridDim.y;
+  const int w_begin = blockIdx.y * w_chunk, w_end = min(Wo, w_begin + w_chunk);
+  const int rows = p.T_out * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int t = row / Ho, h = row - t * Ho;
+    const __nv_bfloat16* srow = p.x + (static_cast<long long>(p.t_src[t]) * p.H + (h >> 1)) * p.W * C + v * 8;
+    __nv_bfloat16* orow = p.out + static_cast<long long>(row) * Wo * C + v * 8;
+#pragma unroll 4
+    for (int w = w_begin + slot; w < w_end; w += ppi)
+      *reinterpret_cast<uint4*>(orow + static_cast<long long>(w) * C) =
+          __ldg(reinterpret_cast<const uint4*>(srow + static_cast<long long>(w >> 1) * C));
   }
 }
 
@@ -265,7 +314,7 @@ extern "C" int vgpa_spatialnorm_apply_bf16(const vgpa_spatialnorm_args* a, void*
   using namespace vgpa;
   VGPA_CHECK(a != nullptr, "vgpa_spatialnorm_apply_bf16: null args");
   VGPA_CHECK(a->x && a->out && a->mean_rstd && a->gamma && a->beta && a->y_lat && a->b_lat, "vgpa_spatialnorm_apply_bf16: null pointer");
-  VGPA_CHECK(a->T > 0 && a->T <= 16 && a->H > 0 && a->W > 0 && a->C > 0 && a->C % 8 == 0, "vgpa_spatialnorm_apply_bf16: bad shape");
+  VGPA_CHECK(a->T > 0 && a->T <= 16 && a->H > 0 && a->W > 0 && a->C > 0 && a->C % 8 == 0 && a->C <= 2048, "vgpa_spatialnorm_apply_bf16: bad shape");
   VGPA_CHECK(a->groups > 0 && a->C % a->groups == 0, "vgpa_spatialnorm_apply_bf16: bad groups");
   VGPA_CHECK(a->ld_lat >= a->C && a->ld_lat % 8 == 0, "vgpa_spatialnorm_apply_bf16: ld_lat=%lld invalid", (long long)a->ld_lat);
   VGPA_CHECK(a->shift >= 0 && ((a->H - 1) >> a->shift) < a->Hz && ((a->W - 1) >> a->shift) < a->Wz,
@@ -282,8 +331,7 @@ extern "C" int vgpa_spatialnorm_apply_bf16(const vgpa_spatialnorm_args* a, void*
   p.T = a->T; p.H = a->H; p.W = a->W; p.C = a->C; p.groups = a->groups;
   p.Hz = a->Hz; p.Wz = a->Wz; p.shift = a->shift; p.silu = a->silu;
   for (int i = 0; i < 16; ++i) p.tz_of_t[i] = a->tz_of_t[i];
-  const long long n_vec = static_cast<long long>(a->T) * a->H * a->W * (a->C / 8);
-  spatialnorm_apply_kernel<<<grid_for(n_vec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  spatialnorm_apply_kernel<<<row_grid(a->T * a->H, a->W, 256 / (a->C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   VGPA_LAUNCH_CHECK("spatialnorm_apply_kernel");
   return 0;
 }
@@ -292,14 +340,13 @@ extern "C" int vgpa_upsample_nearest_bf16(const void* x, void* out, int T_out, i
                                           void* stream) {
   using namespace vgpa;
   VGPA_CHECK(x && out && t_src_host, "vgpa_upsample_nearest_bf16: null pointer");
-  VGPA_CHECK(T_out > 0 && T_out <= 16 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "vgpa_upsample_nearest_bf16: bad shape");
+  VGPA_CHECK(T_out > 0 && T_out <= 16 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 2048, "vgpa_upsample_nearest_bf16: bad shape");
   UpParams p;
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.T_out = T_out; p.H = H; p.W = W; p.C = C;
   for (int i = 0; i < 16; ++i) p.t_src[i] = i < T_out ? t_src_host[i] : 0;
-  const long long n_vec = static_cast<long long>(T_out) * 4 * H * W * (C / 8);
-  upsample_nearest_kernel<<<grid_for(n_vec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  upsample_nearest_kernel<<<row_grid(T_out * 2 * H, 2 * W, 256 / (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   VGPA_LAUNCH_CHECK("upsample_nearest_kernel");
   return 0;
 }
