@@ -257,3 +257,153 @@ def decode(sd, cfg: VAEConfig, z, tiling: bool = True):
             result_row.append(tile[:, :, :, :geo["limit_h"], :geo["limit_w"]])
         result_rows.append(torch.cat(result_row, dim=4))
     return torch.cat(result_rows, dim=3)
+
+
+# ====================================================================== encoder
+# Restates diffusers' CogVideoXEncoder3D / AutoencoderKLCogVideoX.encode as the reference's latent encoders drive it
+# (`train/CogVideoX-5B/02_encode.py:108-115`: `vae.encode(video).latent_dist.sample()`; the I2V pipeline encodes the first
+# frame the same way). Like the decoder this is recalled from the library: **parity unpinned**.
+#   * CogVideoXDownBlock3D: `layers_per_block` resnets with plain GroupNorm(32, eps 1e-6) (no spatial conditioning), then
+#     CogVideoXDownsample3D on all but the last block: when compress_time, avg_pool1d(kernel 2, stride 2) over time (an odd
+#     frame count keeps the first frame and pools the rest), then F.pad(0,1,0,1) + per-frame Conv2d 3x3 stride 2.
+#   * mid block: 2 resnets; norm_out GroupNorm -> SiLU -> conv_out to 2 * latent_channels (mean, logvar).
+#   * frame batching: 8 sample frames per encoder call, the first call takes the remainder (49 -> 9 + 5 x 8), conv caches
+#     carried across calls; tiling: sample tiles 240 x 360 with stride 200 x 288, latent blend extents 5 / 9, crop 25 x 36.
+#   * DiagonalGaussianDistribution: logvar clamped to [-30, 20]; sample = mean + exp(0.5 logvar) * noise.
+NUM_SAMPLE_FRAMES_BATCH_SIZE = 8
+
+
+def random_encoder_state_dict(cfg: VAEConfig, seed: int = 98, dtype=torch.float32, in_channels: int = 3) -> dict:
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, co, ci, *k):
+        fan = ci
+        for kk in k:
+            fan *= kk
+        sd[name + ".weight"] = (torch.randn(co, ci, *k, generator=g) * (1.0 / fan) ** 0.5).to(dtype)
+        sd[name + ".bias"] = (torch.randn(co, generator=g) * 0.02).to(dtype)
+
+    def gn(name, c):
+        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(c, generator=g)).to(dtype)
+        sd[name + ".bias"] = (0.05 * torch.randn(c, generator=g)).to(dtype)
+
+    def resnet(name, ci, co):
+        gn(name + ".norm1", ci)
+        conv(name + ".conv1.conv", co, ci, 3, 3, 3)
+        gn(name + ".norm2", co)
+        conv(name + ".conv2.conv", co, co, 3, 3, 3)
+        if ci != co:
+            conv(name + ".conv_shortcut", co, ci, 1, 1, 1)
+
+    boc = cfg.block_out_channels
+    conv("encoder.conv_in.conv", boc[0], in_channels, 3, 3, 3)
+    cin = boc[0]
+    for i, co in enumerate(boc):
+        for j in range(cfg.layers_per_block):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else co, co)
+        if i != len(boc) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", co, co, 3, 3)
+        cin = co
+    for j in range(2):
+        resnet(f"encoder.mid_block.resnets.{j}", boc[-1], boc[-1])
+    gn("encoder.norm_out", boc[-1])
+    conv("encoder.conv_out.conv", 2 * cfg.latent_channels, boc[-1], 3, 3, 3)
+    return sd
+
+
+def gn_resnet_block(sd, name, x, groups, cache_in, cache_out):
+    h = F.group_norm(x, groups, sd[name + ".norm1.weight"].to(x.dtype), sd[name + ".norm1.bias"].to(x.dtype), eps=1e-6)
+    h = causal_conv3d(sd, name + ".conv1.conv", F.silu(h), cache_in, cache_out)
+    h = F.group_norm(h, groups, sd[name + ".norm2.weight"].to(x.dtype), sd[name + ".norm2.bias"].to(x.dtype), eps=1e-6)
+    h = causal_conv3d(sd, name + ".conv2.conv", F.silu(h), cache_in, cache_out)
+    if name + ".conv_shortcut.weight" in sd:
+        x = F.conv3d(x, sd[name + ".conv_shortcut.weight"].to(x.dtype), sd[name + ".conv_shortcut.bias"].to(x.dtype))
+    return x + h
+
+
+def downsample3d(sd, name, x, compress_time: bool):
+    B, C, T, H, W = x.shape
+    if compress_time:
+        y = x.permute(0, 3, 4, 1, 2).reshape(B * H * W, C, T)
+        if T % 2 == 1:
+            first, rest = y[..., 0], y[..., 1:]
+            if rest.shape[-1] > 0:
+                rest = F.avg_pool1d(rest, kernel_size=2, stride=2)
+            y = torch.cat([first[..., None], rest], dim=-1)
+        else:
+            y = F.avg_pool1d(y, kernel_size=2, stride=2)
+        T = y.shape[-1]
+        x = y.reshape(B, H, W, C, T).permute(0, 3, 4, 1, 2)
+    x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
+    y = x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H + 1, W + 1)
+    y = F.conv2d(y, sd[name + ".conv.weight"].to(x.dtype), sd[name + ".conv.bias"].to(x.dtype), stride=2)
+    return y.reshape(B, T, -1, y.shape[-2], y.shape[-1]).permute(0, 2, 1, 3, 4)
+
+
+def encoder_forward(sd, cfg: VAEConfig, x, cache_in: dict | None):
+    """CogVideoXEncoder3D.forward(sample=x, conv_cache) -> (moments [B, 2*latent, T', h, w], new conv_cache)."""
+    cache_out = _Cache()
+    g = cfg.norm_num_groups
+    boc = cfg.block_out_channels
+    h = causal_conv3d(sd, "encoder.conv_in.conv", x, cache_in, cache_out)
+    for i in range(len(boc)):
+        for j in range(cfg.layers_per_block):
+            h = gn_resnet_block(sd, f"encoder.down_blocks.{i}.resnets.{j}", h, g, cache_in, cache_out)
+        if i != len(boc) - 1:
+            h = downsample3d(sd, f"encoder.down_blocks.{i}.downsamplers.0", h, compress_time=i < cfg.temporal_compress_level)
+    for j in range(2):
+        h = gn_resnet_block(sd, f"encoder.mid_block.resnets.{j}", h, g, cache_in, cache_out)
+    h = F.group_norm(h, g, sd["encoder.norm_out.weight"].to(h.dtype), sd["encoder.norm_out.bias"].to(h.dtype), eps=1e-6)
+    h = causal_conv3d(sd, "encoder.conv_out.conv", F.silu(h), cache_in, cache_out)
+    return h, cache_out
+
+
+def encode_untiled(sd, cfg: VAEConfig, x):
+    cache = None
+    outs = []
+    for (s, e) in frame_batches(x.shape[2], NUM_SAMPLE_FRAMES_BATCH_SIZE):
+        o, cache = encoder_forward(sd, cfg, x[:, :, s:e], cache)
+        outs.append(o)
+    return torch.cat(outs, dim=2)
+
+
+def encode_tiling_geometry(cfg: VAEConfig):
+    th, tw = cfg.tile_sample_min_height, cfg.tile_sample_min_width
+    bh = int(cfg.tile_latent_min_height * cfg.tile_overlap_factor_height)
+    bw = int(cfg.tile_latent_min_width * cfg.tile_overlap_factor_width)
+    return dict(tile_h=th, tile_w=tw,
+                overlap_h=int(th * (1 - cfg.tile_overlap_factor_height)), overlap_w=int(tw * (1 - cfg.tile_overlap_factor_width)),
+                blend_h=bh, blend_w=bw, limit_h=cfg.tile_latent_min_height - bh, limit_w=cfg.tile_latent_min_width - bw)
+
+
+def encode(sd, cfg: VAEConfig, x, tiling: bool = True):
+    """AutoencoderKLCogVideoX.encode(x).latent_dist.parameters for x [B, 3, T, H, W]: the moments (mean | logvar)."""
+    B, C, T, H, W = x.shape
+    geo = encode_tiling_geometry(cfg)
+    if not (tiling and (W > geo["tile_w"] or H > geo["tile_h"])):
+        return encode_untiled(sd, cfg, x)
+    rows = []
+    for i in range(0, H, geo["overlap_h"]):
+        row = []
+        for j in range(0, W, geo["overlap_w"]):
+            row.append(encode_untiled(sd, cfg, x[:, :, :, i:i + geo["tile_h"], j:j + geo["tile_w"]]))
+        rows.append(row)
+    result_rows = []
+    for i, row in enumerate(rows):
+        result_row = []
+        for j, tile in enumerate(row):
+            if i > 0:
+                tile = blend_v(rows[i - 1][j], tile, geo["blend_h"])
+            if j > 0:
+                tile = blend_h(row[j - 1], tile, geo["blend_w"])
+            result_row.append(tile[:, :, :, :geo["limit_h"], :geo["limit_w"]])
+        result_rows.append(torch.cat(result_row, dim=4))
+    return torch.cat(result_rows, dim=3)
+
+
+def gaussian_sample(moments, noise):
+    """DiagonalGaussianDistribution(moments).sample() with the noise passed in (the library draws it with randn_tensor)."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return mean + torch.exp(0.5 * logvar) * noise

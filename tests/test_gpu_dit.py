@@ -251,12 +251,14 @@ def test_generate_cli_1_5_synthetic(lib, tmp_path, capsys):
 
 
 def test_generate_cli_i2v_synthetic(lib, tmp_path, capsys):
-    """generate/CogVideoX-5B-I2V.py surface on the GPU: first-frame latent channel-concat (in_channels 32 + learned positional
+    """generate/CogVideoX-5B-I2V.py surface on the GPU: first frame through the VAE encoder, latent channel-concat (in_channels 32 + learned positional
     embedding), `--base_dir` image resolution, missing image -> skipped, item without image -> ignored."""
     import json
     from videogpa_b200.generate import cogvideox_5b_i2v as g
     (tmp_path / "imgs").mkdir()
-    (tmp_path / "imgs" / "a.png").write_bytes(b"not really a png, only hashed in synthetic mode")
+    import cv2
+    import numpy as np
+    cv2.imwrite(str(tmp_path / "imgs" / "a.png"), np.random.default_rng(0).integers(0, 255, (120, 200, 3), dtype=np.uint8))
     pj = tmp_path / "p.json"
     pj.write_text(json.dumps({"s1": {"text_prompt": "a boat", "image_prompt": "a.png"}, "s2": {"text_prompt": "a car", "image_prompt": "missing.png"},
                               "s3": {"text_prompt": "no image"}}))

@@ -187,6 +187,27 @@ def test_decoder_tiled_vs_oracle(lib):
     assert (out2 - out).abs().max().item() > 10 * err.mean().item()
 
 
+def test_decoder_streams_and_graph_are_bit_identical(lib):
+    """Tiles on 1 / 4 streams and the CUDA-graph replay run the same kernels in the same per-tile order: same bits."""
+    cfg = small_cfg()
+    sd = _bf16_sd(V.random_state_dict(cfg, seed=14))
+    dec = make_decoder(cfg, sd)
+    dec.enable_tiling(); dec.enable_slicing()
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(1, 16, 3, 12, 20, generator=g).to(BF).cuda()
+    dec.tile_streams = 1
+    base = dec.decode(z).sample.clone()
+    dec.tile_streams = 4
+    assert torch.equal(dec.decode(z).sample, base)
+    dec.enable_cuda_graph()
+    assert torch.equal(dec.decode(z).sample, base)             # capture + first replay
+    z2 = torch.randn(1, 16, 3, 12, 20, generator=g).to(BF).cuda()
+    got2 = dec.decode(z2).sample.clone()                       # replay with new input
+    dec.enable_cuda_graph(False)
+    assert torch.equal(dec.decode(z2).sample, got2)
+    assert not torch.equal(got2, base)
+
+
 def test_decoder_rejects_cpu_and_bad_shapes(lib):
     cfg = small_cfg()
     dec = make_decoder(cfg, V.random_state_dict(cfg, seed=13))
@@ -194,3 +215,104 @@ def test_decoder_rejects_cpu_and_bad_shapes(lib):
         dec.decode(torch.zeros(1, 16, 1, 6, 10))
     with pytest.raises(RuntimeError):
         dec.decode(torch.zeros(1, 8, 1, 6, 10, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------- encoder (row f-4)
+def make_encoder(cfg, sd):
+    from videogpa_b200.vae import AutoencoderKLCogVideoXEncoder, VAEDecoderConfig
+    dcfg = VAEDecoderConfig(block_out_channels=cfg.block_out_channels, sample_height=cfg.sample_height, sample_width=cfg.sample_width)
+    return AutoencoderKLCogVideoXEncoder(sd, dcfg, device="cuda")
+
+
+def _check_moments(out, ref):
+    """Whole-encoder tolerance: ~25 bf16 layers deep against the fp32 oracle on bf16-rounded weights."""
+    assert out.shape == ref.shape
+    err = (out - ref).abs()
+    assert relmax(out, ref) < 6e-2 and err.mean().item() < 1e-2 * ref.abs().max().item(), (relmax(out, ref), err.mean().item())
+
+
+def test_encoder_untiled_vs_oracle(lib):
+    cfg = small_cfg()
+    sd = _bf16_sd(V.random_encoder_state_dict(cfg, seed=21))
+    enc = make_encoder(cfg, sd)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(1, 3, 17, 48, 80, generator=g) * 2 - 1).to(BF)                 # 17 frames: passes of 9 + 8 -> 3 + 2 latents
+    dist = enc.encode(x.cuda()).latent_dist
+    ref = V.encode(sd, cfg, x.float(), tiling=False)
+    assert ref.shape == (1, 32, 5, 6, 10)
+    _check_moments(dist.parameters.cpu().float(), ref)
+    # DiagonalGaussianDistribution: mode = mean, sample = mean + std * noise with the clamp on logvar
+    assert torch.equal(dist.mode(), dist.parameters[:, :16])
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    s = dist.sample(generator=gen)
+    gen.manual_seed(7)
+    noise = torch.randn(dist.mean.shape, generator=gen, device="cuda", dtype=dist.mean.dtype)
+    assert torch.equal(s, V.gaussian_sample(dist.parameters, noise))
+
+
+def test_encoder_single_image_and_even_frames(lib):
+    """The I2V first frame (T = 1: no temporal pooling) and an even frame count (pool pairs, no kept first frame)."""
+    cfg = small_cfg()
+    sd = _bf16_sd(V.random_encoder_state_dict(cfg, seed=22))
+    enc = make_encoder(cfg, sd)
+    g = torch.Generator().manual_seed(4)
+    for T, Tl in ((1, 1), (8, 2)):
+        x = (torch.rand(1, 3, T, 48, 80, generator=g) * 2 - 1).to(BF)
+        out = enc.encode(x.cuda()).latent_dist.parameters.cpu().float()
+        ref = V.encode(sd, cfg, x.float(), tiling=False)
+        assert ref.shape == (1, 32, Tl, 6, 10)
+        _check_moments(out, ref)
+
+
+def test_encoder_tiled_vs_oracle(lib):
+    cfg = small_cfg()
+    sd = _bf16_sd(V.random_encoder_state_dict(cfg, seed=23))
+    enc = make_encoder(cfg, sd)
+    enc.enable_tiling()
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(1, 3, 9, 96, 160, generator=g) * 2 - 1).to(BF)                 # 3x3 sample tiles of 48x80, stride 40x64
+    out = enc.encode(x.cuda()).latent_dist.parameters.cpu().float()
+    ref = V.encode(sd, cfg, x.float(), tiling=True)
+    assert ref.shape == (1, 32, 3, 12, 20)
+    _check_moments(out, ref)
+    enc.disable_tiling()                                                           # per-tile GroupNorm statistics change the result
+    out2 = enc.encode(x.cuda()).latent_dist.parameters.cpu().float()
+    assert (out2 - out).abs().max().item() > 0
+
+
+def test_encoder_rejects_bad_input(lib):
+    cfg = small_cfg()
+    enc = make_encoder(cfg, V.random_encoder_state_dict(cfg, seed=24))
+    with pytest.raises(RuntimeError):
+        enc.encode(torch.zeros(1, 3, 1, 48, 80))                                   # CPU tensor
+    with pytest.raises(RuntimeError):
+        enc.encode(torch.zeros(1, 4, 1, 48, 80, device="cuda"))                    # wrong channel count
+    with pytest.raises(RuntimeError):
+        enc.encode(torch.zeros(1, 3, 1, 50, 80, device="cuda"))                    # not a multiple of 8
+    sd = V.random_encoder_state_dict(cfg, seed=24)
+    del sd["encoder.norm_out.weight"]
+    with pytest.raises(RuntimeError):
+        make_encoder(cfg, sd)
+
+
+def test_encode_video_latent_mirror(lib):
+    """videogpa_b200.encode.encode_video_latent = the tensor half of train/CogVideoX-5B/02_encode.py:97-123: frames
+    sampled by truncated linspace, scaled to [0, 1] (not [-1, 1]), sampled latent moved to the host; the 1.5 variant
+    multiplies by scaling_factor."""
+    from videogpa_b200.encode import encode_video_latent, select_frame_indices
+    cfg = small_cfg()
+    sd = _bf16_sd(V.random_encoder_state_dict(cfg, seed=25))
+    enc = make_encoder(cfg, sd)
+    frames = np.random.default_rng(1).integers(0, 256, (20, 48, 80, 3), dtype=np.uint8)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    lat = encode_video_latent(enc, frames, num_frames=9, generator=gen)
+    assert lat.device.type == "cpu" and lat.shape == (16, 3, 6, 10)
+    x = (torch.from_numpy(frames[select_frame_indices(20, 9)]).float() / 255.0).permute(3, 0, 1, 2)[None].to(BF)
+    ref_m = V.encode(sd, cfg, x.float(), tiling=False)
+    gen.manual_seed(11)
+    noise = torch.randn((1, 16, 3, 6, 10), generator=gen, device="cuda", dtype=BF).cpu().float()
+    ref = V.gaussian_sample(ref_m, noise)[0]
+    assert relmax(lat.float(), ref) < 6e-2
+    gen.manual_seed(11)
+    lat15 = encode_video_latent(enc, frames, num_frames=9, scale_latents=True, generator=gen)
+    assert torch.allclose(lat15.float(), lat.float() * 0.7, rtol=1e-2, atol=1e-3)

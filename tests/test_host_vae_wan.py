@@ -74,3 +74,39 @@ def test_c_abi_argument_validation_of_new_entry_points(lib):
     at.q = at.k = at.v = at.out = 0x1000
     at.B, at.H, at.Sq, at.Skv, at.head_dim = 1, 1, 8, 8, 96
     assert lib.vgpa_attention_bf16(C.byref(at), None) != 0 and b"head_dim must be 64 or 128" in lib.vgpa_last_error()
+
+
+def test_encode_frame_selection_matches_reference_rule():
+    """train/CogVideoX-5B/02_encode.py:55-63: short clips keep every frame, long clips use truncated linspace; frames are
+    scaled to [0, 1] and laid out [3, F, H, W]."""
+    import numpy as np
+    from videogpa_b200.encode import frames_to_video_tensor, select_frame_indices
+    assert select_frame_indices(10, 49).tolist() == list(range(10))
+    assert select_frame_indices(49, 49).tolist() == list(range(49))
+    idx = select_frame_indices(120, 49)
+    assert idx.tolist() == np.linspace(0, 119, 49).astype(int).tolist() and idx[0] == 0 and idx[-1] == 119
+    fr = np.random.default_rng(0).integers(0, 256, (60, 4, 6, 3), dtype=np.uint8)
+    v = frames_to_video_tensor(fr, 49, device="cpu")
+    assert v.shape == (3, 49, 4, 6) and float(v.max()) <= 1.0 and float(v.min()) >= 0.0
+    assert torch.equal(v[:, 5], torch.from_numpy(fr[select_frame_indices(60, 49)[5]]).float().div(255).permute(2, 0, 1))
+    with pytest.raises(RuntimeError):
+        frames_to_video_tensor(np.zeros((4, 4, 4), dtype=np.uint8), 49, device="cpu")
+
+
+def test_encoder_oracle_shapes_and_tiling_geometry():
+    """Oracle-side invariants of the VAE encoder restatement: 49 frames -> passes of 9 + 5 x 8 -> 13 latent frames; full-size
+    tiling geometry (sample tiles 240 x 360, stride 200 x 288, latent blend 5 / 9, crop 25 x 36)."""
+    from oracle import vae_torch as V
+    assert V.frame_batches(49, V.NUM_SAMPLE_FRAMES_BATCH_SIZE) == [(0, 9), (9, 17), (17, 25), (25, 33), (33, 41), (41, 49)]
+    geo = V.encode_tiling_geometry(V.VAEConfig())
+    assert geo == dict(tile_h=240, tile_w=360, overlap_h=200, overlap_w=288, blend_h=5, blend_w=9, limit_h=25, limit_w=36)
+    cfg = V.VAEConfig(block_out_channels=(32, 32, 32, 32), layers_per_block=1, sample_height=32, sample_width=32)
+    sd = V.random_encoder_state_dict(cfg, seed=1)
+    x = torch.rand(1, 3, 9, 16, 16, generator=torch.Generator().manual_seed(0))
+    m = V.encode(sd, cfg, x, tiling=False)
+    assert m.shape == (1, 32, 3, 2, 2)
+    # causal across passes: a 17-frame clip is encoded as passes of 9 + 8 frames, so its first 3 latent frames equal the
+    # 9-frame clip's (GroupNorm statistics are per pass, conv caches only flow forward)
+    x17 = torch.cat([x, torch.rand(1, 3, 8, 16, 16, generator=torch.Generator().manual_seed(1))], dim=2)
+    m17 = V.encode(sd, cfg, x17, tiling=False)
+    assert m17.shape == (1, 32, 5, 2, 2) and torch.allclose(m17[:, :, :3], m, atol=1e-6)

@@ -252,6 +252,15 @@ extern "C" int vgpa_conv3d_causal_bf16(const vgpa_conv3d_args* a, void* stream) 
   else if (a->Cout_pad == 64) BN = 64;
   else if (a->Cout_pad == 16) BN = 16;
   VGPA_CHECK(BN != 0, "vgpa_conv3d_causal_bf16: Cout_pad=%d must be 16, 64, 128 or a multiple of 256", a->Cout_pad);
+  if (BN == 256) {
+    // low-resolution layers have fewer 128x256 output tiles than SMs (30x45x2 frames, 512 channels: 48): halve the
+    // N tile when that shortens the schedule. A 128x128 tile costs ~0.58 of a 128x256 one (its MMAs are bound by the
+    // shared-memory operand reads, not the tensor pipe).
+    const long long m_tiles = static_cast<long long>(a->T) * ((a->H + CV_TH - 1) / CV_TH) * ((a->W + CV_TW - 1) / CV_TW);
+    const long long it256 = m_tiles * (a->Cout_pad / 256), it128 = 2 * it256;
+    const double c256 = static_cast<double>((it256 + 147) / 148), c128 = 0.58 * static_cast<double>((it128 + 147) / 148);
+    if (c128 < c256) BN = 128;
+  }
   VGPA_CHECK(a->Cout % 16 == 0 || a->Cout_pad == 16, "vgpa_conv3d_causal_bf16: Cout=%d must be a multiple of 16 (or Cout_pad 16)", a->Cout);
   VGPA_CHECK(a->ldo % 8 == 0 && a->ldo >= (a->Cout_pad == 16 ? 16 : a->Cout), "vgpa_conv3d_causal_bf16: ldo=%d invalid", a->ldo);
   VGPA_CHECK(a->residual == nullptr || (a->ld_res % 8 == 0 && a->ld_res >= a->Cout), "vgpa_conv3d_causal_bf16: ld_res=%d invalid", a->ld_res);

@@ -97,7 +97,8 @@ class _SyntheticPrompts:
         return torch.randn(1, max_len, self.dim, generator=g).to(self.device, torch.bfloat16)
 
 
-def build_pipeline(args, device):
+def build_pipeline(args, device, with_encoder: bool = False):
+    """-> (pipeline, prompt encoder). `with_encoder` also builds the VAE encoder (I2V first frame) as `pipe.vae_encoder`."""
     from ..pipeline import CogVideoXDenoisePipeline
     from ..schedulers import CogVideoXDPMScheduler
     from ..transformer import CogVideoXTransformer3D, TransformerConfig
@@ -119,11 +120,21 @@ def build_pipeline(args, device):
         vcfg = json.loads((base / "vae" / "config.json").read_text())
         vknown = VAEDecoderConfig.__dataclass_fields__.keys()
         vkw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in vcfg.items() if k in vknown}
-        vae = AutoencoderKLCogVideoXDecoder(_load_safetensors_dir(base / "vae"), VAEDecoderConfig(**vkw), device=device)
+        vae_sd = _load_safetensors_dir(base / "vae")
+        vae = AutoencoderKLCogVideoXDecoder(vae_sd, VAEDecoderConfig(**vkw), device=device)
         prompts = _T5Prompts(base, device)
     vae.enable_tiling()
     vae.enable_slicing()
     pipe = CogVideoXDenoisePipeline(transformer, CogVideoXDPMScheduler(), vae=vae, vae_scaling_factor=vae.config.scaling_factor)
+    pipe.vae_encoder = None
+    if with_encoder:
+        from ..vae import AutoencoderKLCogVideoXEncoder
+        if args.synthetic:
+            pipe.vae_encoder = AutoencoderKLCogVideoXEncoder.random_init(VAEDecoderConfig(), seed=6, device=device)
+        else:
+            pipe.vae_encoder = AutoencoderKLCogVideoXEncoder(vae_sd, VAEDecoderConfig(**vkw), device=device)
+        pipe.vae_encoder.enable_tiling()                            # pipe.vae.enable_tiling() covers encode in the library
+        pipe.vae_encoder.enable_slicing()
     return pipe, prompts
 
 

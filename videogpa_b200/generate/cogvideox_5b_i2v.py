@@ -4,14 +4,13 @@ Reference: generate/CogVideoX-5B-I2V.py:12-115: the T2V flags plus `--base_dir` 
 `(group_id, {text_prompt, image_prompt | image_path | input_image_path})`; items without a prompt or an image are
 skipped, a missing image prints `Image not found ... skipping`; the checkpoint's default (DDIM) scheduler is kept.
 The I2V transformer (in_channels 32, learned positional embedding) and the channel-concat of the encoded first frame run
-on videogpa_b200 kernels. The first-frame latent comes from the VAE *encoder*, which is a "next" row
-and not built: with a real checkpoint the CLI looks for a pre-computed `<image>.latent.pt` ([16, 1, h, w], already
-multiplied by scaling_factor) next to the image; `--synthetic N` derives a hash-seeded latent from the image bytes so the
-CLI contract can be exercised without checkpoints.
+on videogpa_b200 kernels. The first-frame latent is `vae.encode(image).latent_dist.sample(generator) * scaling_factor`
+as in the library's I2V `prepare_latents` (resize to width x height, [-1, 1]), drawn from the prompt's generator BEFORE
+the initial noise; the remaining F-1 latent frames are zero. `--synthetic N` runs the same flow with seeded random
+transformer / VAE weights so the CLI contract can be exercised without checkpoints.
 """
 from __future__ import annotations
 
-import hashlib
 import json
 import os
 from pathlib import Path
@@ -42,22 +41,26 @@ def resolve_image(item: dict, base_dir: str | None) -> str:
     return image_path
 
 
-def first_frame_latent(image_path: str, shape, device, synthetic: bool) -> torch.Tensor:
+def load_image_tensor(image_path: str, height: int, width: int) -> torch.Tensor:
+    """diffusers `load_image` + VideoProcessor.preprocess: RGB, resized to (width, height) (lanczos), [-1, 1], [3, H, W]."""
+    import numpy as np
+    from PIL import Image
+    img = Image.open(image_path).convert("RGB").resize((width, height), Image.LANCZOS)
+    return torch.from_numpy(np.asarray(img).copy()).permute(2, 0, 1).float() / 127.5 - 1.0
+
+
+def first_frame_latent(image_path: str, shape, device, encoder, scaling_factor: float, generator=None,
+                       height: int | None = None, width: int | None = None) -> torch.Tensor:
     """-> image latents [1, F, 16, h, w]: the encoded first frame followed by F-1 zero frames (App. A.4)."""
     F_, C, h, w = shape
-    if synthetic:
-        seed = int.from_bytes(hashlib.sha256(Path(image_path).read_bytes()).digest()[:4], "little")
-        first = torch.randn(C, 1, h, w, generator=torch.Generator().manual_seed(seed))
-    else:
-        pre = Path(str(image_path) + ".latent.pt")
-        if not pre.exists():
-            raise RuntimeError(f"{pre} not found: the VAE encoder is not part of this build (SURVEY.md §8 f-4); "
-                               "provide the scaled first-frame latent [16, 1, h, w]")
-        first = torch.load(str(pre), map_location="cpu")
-        if tuple(first.shape) != (C, 1, h, w):
-            raise RuntimeError(f"{pre}: expected shape {(C, 1, h, w)}, got {tuple(first.shape)}")
+    if encoder is None:
+        raise RuntimeError("the I2V pipeline needs the VAE encoder")
+    img = load_image_tensor(image_path, height or h * 8, width or w * 8).to(device=device, dtype=torch.bfloat16)
+    first = encoder.encode(img[None, :, None]).latent_dist.sample(generator=generator)[0] * scaling_factor     # [C, 1, h, w]
+    if tuple(first.shape) != (C, 1, h, w):
+        raise RuntimeError(f"encoded first frame has shape {tuple(first.shape)}, expected {(C, 1, h, w)}")
     lat = torch.zeros(1, F_, C, h, w, dtype=torch.bfloat16, device=device)
-    lat[0, 0] = first[:, 0].to(device=device, dtype=torch.bfloat16)
+    lat[0, 0] = first[:, 0].to(torch.bfloat16)
     return lat
 
 
@@ -77,7 +80,7 @@ def generate(args):
     if args.synthetic:
         from ..pipeline import CogVideoXDenoisePipeline
         from ..transformer import CogVideoXTransformer3D, TransformerConfig
-        from ..vae import AutoencoderKLCogVideoXDecoder, VAEDecoderConfig
+        from ..vae import AutoencoderKLCogVideoXDecoder, AutoencoderKLCogVideoXEncoder, VAEDecoderConfig
         cfg = TransformerConfig.cogvideox_5b_i2v()
         cfg.num_layers = args.synthetic
         cfg.sample_height, cfg.sample_width = args.height // 8, args.width // 8
@@ -86,9 +89,11 @@ def generate(args):
         vae.enable_tiling(); vae.enable_slicing()
         pipe = CogVideoXDenoisePipeline(CogVideoXTransformer3D.random_init(cfg, seed=1234, device=device), CogVideoXDDIMScheduler(), vae=vae,
                                         vae_scaling_factor=vae.config.scaling_factor)
+        pipe.vae_encoder = AutoencoderKLCogVideoXEncoder.random_init(VAEDecoderConfig(), seed=6, device=device)
+        pipe.vae_encoder.enable_tiling(); pipe.vae_encoder.enable_slicing()
         prompts = base._SyntheticPrompts(cfg.text_embed_dim, device)
     else:
-        pipe, prompts = base.build_pipeline(args, device)
+        pipe, prompts = base.build_pipeline(args, device, with_encoder=True)
         pipe.scheduler = CogVideoXDDIMScheduler()                   # the I2V script keeps the checkpoint default (:18-19)
     if args.lora_path:
         if not os.path.exists(args.lora_path):
@@ -124,7 +129,8 @@ def generate(args):
         try:
             generator = torch.Generator(device=device).manual_seed(args.seed)
             _, F_, C, h, w = pipe.latent_shape(1, args.num_frames, args.height, args.width)
-            img_lat = first_frame_latent(image_path, (F_, C, h, w), device, bool(args.synthetic))
+            img_lat = first_frame_latent(image_path, (F_, C, h, w), device, pipe.vae_encoder, pipe.vae.config.scaling_factor,
+                                         generator=generator, height=args.height, width=args.width)
             frames = pipe(prompts(text_prompt), negative, num_frames=args.num_frames, height=args.height, width=args.width,
                           num_inference_steps=args.num_inference_steps, guidance_scale=args.guidance_scale, generator=generator,
                           image_latents=img_lat, output_type="pt")

@@ -39,6 +39,8 @@ class VAEDecoderConfig:
     sample_height: int = 480
     sample_width: int = 720
     num_latent_frames_batch_size: int = 2
+    num_sample_frames_batch_size: int = 8
+    in_channels: int = 3
     tile_overlap_factor_height: float = 1 / 6
     tile_overlap_factor_width: float = 1 / 5
 
@@ -58,6 +60,8 @@ class _SNorm:
 def _pad_cout(c: int) -> int:
     if c % 256 == 0 or c in (64, 128):
         return c
+    if c in (32, 48):                                # encoder conv_out: 2 * latent_channels moments
+        return 64
     if c <= 16:
         return 16
     raise RuntimeError(f"VAE conv with {c} output channels is not supported (need 64, 128 or a multiple of 256)")
@@ -72,6 +76,9 @@ class AutoencoderKLCogVideoXDecoder:
         self.use_slicing = False
         self.tile_streams = 4           # latent tiles are independent: decode them on this many CUDA streams side by side
         self._streams = None
+        self.use_cuda_graph = False
+        self._graphs = {}
+        self._capturing = False
         c = self.config
         self.rc = tuple(reversed(c.block_out_channels))
         self.temporal_compress_level = int(math.log2(c.temporal_compression_ratio))
@@ -402,6 +409,41 @@ class AutoencoderKLCogVideoXDecoder:
             raise RuntimeError("decode needs a CUDA tensor (no CPU fallback exists)")
         if z.dim() != 5 or z.shape[1] != self.config.latent_channels:
             raise RuntimeError(f"z must be [B, {self.config.latent_channels}, T, h, w]")
+        if self.use_cuda_graph:
+            sample = self._decode_graphed(z)
+        else:
+            sample = self._decode_impl(z)
+        if not return_dict:
+            return (sample,)
+        return DecoderOutput(sample=sample)
+
+    def enable_cuda_graph(self, flag: bool = True) -> None:
+        """Replay the whole decode (every tile, frame batch and stream fork/join) as one CUDA graph per latent shape.
+        A tiled 49-frame decode is ~9000 launches of 50-500 us kernels; issued from Python the host is the limiter."""
+        self.use_cuda_graph = bool(flag)
+
+    def _decode_graphed(self, z: torch.Tensor) -> torch.Tensor:
+        key = (tuple(z.shape), z.dtype, self.use_tiling, self.use_slicing, self.tile_streams)
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._decode_impl(z)                                 # eager pass: lazy buffers / streams exist before capture
+            torch.cuda.synchronize(self.device)
+            static_in = z.clone()
+            g = torch.cuda.CUDAGraph()
+            self._capturing = True
+            try:
+                with torch.cuda.graph(g):
+                    static_out = self._decode_impl(static_in)
+            finally:
+                self._capturing = False
+            ent = self._graphs[key] = (g, static_in, static_out)
+        g, static_in, static_out = ent
+        static_in.copy_(z)
+        g.replay()
+        return static_out.clone()
+
+    def _decode_impl(self, z: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
         B, Cz, T, H, W = z.shape
         c = self.config
         zcl = torch.zeros((B, T, H, W, self.zc_pad), dtype=BF16, device=self.device)
@@ -443,8 +485,9 @@ class AutoencoderKLCogVideoXDecoder:
                         tiles.append(self._decode_tile(zcl[b, :, y0:y0 + tlh, x0:x0 + tlw].contiguous()))
                 for st in self._streams[:n_str]:
                     cur.wait_stream(st)
-                for t in tiles:
-                    t.record_stream(cur)
+                if not self._capturing:                          # graph-pool memory is static: nothing to record
+                    for t in tiles:
+                        t.record_stream(cur)
             To = tiles[0].shape[0]
             out = torch.empty((3, To, H * s8, W * s8), dtype=BF16, device=self.device)
             a = ComposeArgs()
@@ -460,10 +503,7 @@ class AutoencoderKLCogVideoXDecoder:
             a.out = out.data_ptr()
             _lib.check(lib.vgpa_vae_compose_tiles_bf16(C.byref(a), _lib.current_stream()), "vgpa_vae_compose_tiles_bf16")
             samples.append(out)
-        sample = torch.stack(samples, 0)
-        if not return_dict:
-            return (sample,)
-        return DecoderOutput(sample=sample)
+        return torch.stack(samples, 0)
 
     # ------------------------------------------------------------------ bookkeeping for bench.py
     def conv_flops(self, T_lat: int, H: int, W: int) -> float:
@@ -486,3 +526,281 @@ class AutoencoderKLCogVideoXDecoder:
             cin = co
         fl += 2.0 * Tcur * h * w * 27 * rc[-1] * self.config.out_channels
         return fl
+
+
+# ====================================================================================================== encoder
+class AutoencoderKLOutput(SimpleNamespace):
+    """`.latent_dist` like diffusers' AutoencoderKLOutput."""
+
+
+class DiagonalGaussianDistribution:
+    """diffusers' DiagonalGaussianDistribution over moments [B, 2C, T, h, w]: logvar clamped to [-30, 20];
+    `sample(generator)` = mean + std * randn, `mode()` = mean (`train/CogVideoX-5B/02_encode.py:113-115`)."""
+
+    def __init__(self, parameters: torch.Tensor):
+        self.parameters = parameters
+        self.mean, logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self, generator: torch.Generator | None = None) -> torch.Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+class AutoencoderKLCogVideoXEncoder:
+    """`vae.encode(x).latent_dist` of diffusers' AutoencoderKLCogVideoX (CogVideoXEncoder3D) on the same kernels as the
+    decoder — SURVEY.md §8 row f-4; reference call sites `train/CogVideoX-5B/02_encode.py:108-115` (video latents) and the
+    first-frame latent of the I2V pipeline (`generate/CogVideoX-5B-I2V.py`).
+
+    Plain GroupNorm + SiLU runs on vgpa_spatialnorm_apply_bf16 with a constant conditioning pair (y = 1, b = 0: both extra
+    roundings are exact); the stride-2 Conv2d of CogVideoXDownsample3D (F.pad(0,1,0,1), no left/top padding) is the
+    stride-1 kernel evaluated at the odd pixel centres; the temporal average pool is two frame-slab adds. Frame batching
+    (8 sample frames per pass, first pass takes the remainder), conv_cache carry-over and the tiled encode (sample tiles
+    240x360, stride 200x288, latent blend 5 / 9, crop 25x36, GroupNorm statistics per tile) follow the library."""
+
+    _conv = AutoencoderKLCogVideoXDecoder._conv
+    _conv_call = AutoencoderKLCogVideoXDecoder._conv_call
+    _gn_stats = AutoencoderKLCogVideoXDecoder._gn_stats
+    _finish_timepad = AutoencoderKLCogVideoXDecoder._finish_timepad
+    frame_batches = staticmethod(AutoencoderKLCogVideoXDecoder.frame_batches)
+    enable_tiling = AutoencoderKLCogVideoXDecoder.enable_tiling
+    disable_tiling = AutoencoderKLCogVideoXDecoder.disable_tiling
+    enable_slicing = AutoencoderKLCogVideoXDecoder.enable_slicing
+    disable_slicing = AutoencoderKLCogVideoXDecoder.disable_slicing
+
+    def __init__(self, state_dict: dict, config: VAEDecoderConfig | None = None, device="cuda"):
+        self.config = c = config or VAEDecoderConfig()
+        self.device = torch.device(device)
+        self.dtype = BF16
+        self.use_tiling = False
+        self.use_slicing = False
+        self._ws = None
+        self.cin_pad = 64
+        if c.in_channels > self.cin_pad or 2 * c.latent_channels > 64:
+            raise RuntimeError("in_channels > 64 or latent_channels > 32 are not supported")
+        self.temporal_compress_level = int(math.log2(c.temporal_compression_ratio))
+        boc = tuple(c.block_out_channels)
+        sd = state_dict
+        self.conv_in = self._conv(sd, "encoder.conv_in.conv", pad_cin_to=self.cin_pad)
+        self.down = []
+        cin = boc[0]
+        for i, co in enumerate(boc):
+            blk = SimpleNamespace()
+            blk.resnets = [self._gn_resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else co, co)
+                           for j in range(c.layers_per_block)]
+            blk.down = None
+            if i != len(boc) - 1:
+                blk.down = self._conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv")
+                blk.compress_time = i < self.temporal_compress_level
+            self.down.append(blk)
+            cin = co
+        self.mid = [self._gn_resnet(sd, f"encoder.mid_block.resnets.{j}", boc[-1], boc[-1]) for j in range(2)]
+        self.norm_out = self._gn(sd, "encoder.norm_out", boc[-1])
+        self.conv_out = self._conv(sd, "encoder.conv_out.conv")
+        cmax = max(boc)
+        self._ones = torch.ones(cmax, dtype=BF16, device=self.device)
+        self._zeros = torch.zeros(cmax, dtype=BF16, device=self.device)
+        self.tile_sample_min_height = c.sample_height // 2
+        self.tile_sample_min_width = c.sample_width // 2
+        self.spatial_scale = 2 ** (len(boc) - 1)
+        self.tile_latent_min_height = int(self.tile_sample_min_height / self.spatial_scale)
+        self.tile_latent_min_width = int(self.tile_sample_min_width / self.spatial_scale)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def random_init(cls, config: VAEDecoderConfig | None = None, seed: int = 6, device="cuda") -> "AutoencoderKLCogVideoXEncoder":
+        """Synthetic encoder weights with the diffusers parameter names (no checkpoint is reachable)."""
+        cfg = config or VAEDecoderConfig()
+        dev = torch.device(device)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        sd = {}
+
+        def conv(name, co, ci, *k):
+            sd[name + ".weight"] = (torch.randn(co, ci, *k, generator=g, device=dev) * (1.0 / (ci * math.prod(k))) ** 0.5).to(BF16)
+            sd[name + ".bias"] = (torch.randn(co, generator=g, device=dev) * 0.02).to(BF16)
+
+        def gn(name, ch):
+            sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(ch, generator=g, device=dev)).to(BF16)
+            sd[name + ".bias"] = (0.05 * torch.randn(ch, generator=g, device=dev)).to(BF16)
+
+        def resnet(name, ci, co):
+            gn(name + ".norm1", ci); conv(name + ".conv1.conv", co, ci, 3, 3, 3)
+            gn(name + ".norm2", co); conv(name + ".conv2.conv", co, co, 3, 3, 3)
+            if ci != co:
+                conv(name + ".conv_shortcut", co, ci, 1, 1, 1)
+
+        boc = tuple(cfg.block_out_channels)
+        conv("encoder.conv_in.conv", boc[0], cfg.in_channels, 3, 3, 3)
+        cin = boc[0]
+        for i, co in enumerate(boc):
+            for j in range(cfg.layers_per_block):
+                resnet(f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else co, co)
+            if i != len(boc) - 1:
+                conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", co, co, 3, 3)
+            cin = co
+        for j in range(2):
+            resnet(f"encoder.mid_block.resnets.{j}", boc[-1], boc[-1])
+        gn("encoder.norm_out", boc[-1])
+        conv("encoder.conv_out.conv", 2 * cfg.latent_channels, boc[-1], 3, 3, 3)
+        return cls(sd, cfg, device=device)
+
+    def _gn(self, sd, name, ch):
+        n = SimpleNamespace()
+        if name + ".weight" not in sd:
+            raise RuntimeError(f"state dict is missing {name}.weight")
+        n.gamma = sd[name + ".weight"].to(device=self.device, dtype=BF16).contiguous()
+        n.beta = sd[name + ".bias"].to(device=self.device, dtype=BF16).contiguous()
+        n.c = ch
+        return n
+
+    def _gn_resnet(self, sd, name, ci, co):
+        r = SimpleNamespace()
+        r.norm1 = self._gn(sd, name + ".norm1", ci)
+        r.conv1 = self._conv(sd, name + ".conv1.conv")
+        r.norm2 = self._gn(sd, name + ".norm2", co)
+        r.conv2 = self._conv(sd, name + ".conv2.conv")
+        r.sc_w = r.sc_b = None
+        if ci != co:
+            w = sd[name + ".conv_shortcut.weight"]
+            if tuple(w.shape[2:]) != (1, 1, 1):
+                raise RuntimeError(f"{name}.conv_shortcut: only the 1x1x1 shortcut of the released checkpoints is supported")
+            r.sc_w = w.reshape(co, ci).to(device=self.device, dtype=BF16).contiguous()
+            r.sc_b = sd[name + ".conv_shortcut.bias"].to(device=self.device, dtype=BF16).contiguous()
+        r.ci, r.co = ci, co
+        return r
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    # ------------------------------------------------------------------ layers
+    def _gn_silu(self, x, norm, out, silu: bool = True):
+        """GroupNorm(32, eps 1e-6)(x) (+ SiLU) -> out, x [T,H,W,C] channels-last."""
+        lib = _lib.load()
+        T, H, W, C_ = x.shape
+        stats = self._gn_stats(x, C_)
+        a = SpatialNormArgs()
+        a.x, a.out, a.mean_rstd = x.data_ptr(), out.data_ptr(), stats.data_ptr()
+        a.gamma, a.beta = norm.gamma.data_ptr(), norm.beta.data_ptr()
+        a.y_lat, a.b_lat, a.ld_lat = self._ones.data_ptr(), self._zeros.data_ptr(), self._ones.numel()
+        a.T, a.H, a.W, a.C, a.groups = T, H, W, C_, self.config.norm_num_groups
+        a.Hz = a.Wz = 1
+        a.shift = 24                                                   # every pixel reads the single constant row
+        a.silu = 1 if silu else 0
+        _lib.check(lib.vgpa_spatialnorm_apply_bf16(C.byref(a), _lib.current_stream()), "vgpa_spatialnorm_apply_bf16")
+
+    def _norm_conv(self, x, norm, cv, key, cache_in, cache_out, residual=None):
+        T, H, W, C_ = x.shape
+        buf = torch.empty((T + 2, H, W, C_), dtype=BF16, device=self.device)
+        self._gn_silu(x, norm, buf[2:])
+        self._finish_timepad(buf, key, cache_in, cache_out)
+        return self._conv_call(cv, buf, T, residual=residual)
+
+    def _resnet_fwd(self, r, x, key, cache_in, cache_out):
+        T, H, W, _ = x.shape
+        h = self._norm_conv(x, r.norm1, r.conv1, key + ".conv1", cache_in, cache_out)
+        res = x
+        if r.sc_w is not None:
+            res = dense.linear(x.view(-1, r.ci), r.sc_w, r.sc_b).view(T, H, W, r.co)
+        return self._norm_conv(h, r.norm2, r.conv2, key + ".conv2", cache_in, cache_out, residual=res)
+
+    def _downsample_fwd(self, blk, x):
+        T = x.shape[0]
+        if blk.compress_time and T > 1:
+            # avg_pool1d(kernel 2, stride 2) over time; an odd frame count keeps the first frame. (a + b) * 0.5 in bf16
+            # rounds once, like the pooled fp32 sum rounded to bf16 (the halving is exact).
+            if T % 2 == 1:
+                x = torch.cat([x[:1], (x[1::2] + x[2::2]) * 0.5], dim=0)
+            else:
+                x = (x[0::2] + x[1::2]) * 0.5
+        full = self._conv_call(blk.down, x.contiguous(), x.shape[0])       # KT = 1: no time padding
+        return full[:, 1::2, 1::2].contiguous()                            # stride 2, window starting at even pixels
+
+    def _encoder_pass(self, xt: torch.Tensor, cache_in: dict | None):
+        """xt [T, H, W, 64] channels-last padded frames -> (moments [T', h, w, 2*latent], conv_cache)."""
+        T = xt.shape[0]
+        cache_out: dict = {}
+        buf = torch.empty((T + 2,) + tuple(xt.shape[1:]), dtype=BF16, device=self.device)
+        buf[2:].copy_(xt)
+        self._finish_timepad(buf, "conv_in", cache_in, cache_out)
+        h = self._conv_call(self.conv_in, buf, T)
+        for i, blk in enumerate(self.down):
+            for j, r in enumerate(blk.resnets):
+                h = self._resnet_fwd(r, h, f"down.{i}.{j}", cache_in, cache_out)
+            if blk.down is not None:
+                h = self._downsample_fwd(blk, h)
+        for j, r in enumerate(self.mid):
+            h = self._resnet_fwd(r, h, f"mid.{j}", cache_in, cache_out)
+        return self._norm_conv(h, self.norm_out, self.conv_out, "conv_out", cache_in, cache_out), cache_out
+
+    def _encode_tile(self, xt: torch.Tensor) -> torch.Tensor:
+        cache = None
+        outs = []
+        for (s, e) in self.frame_batches(xt.shape[0], self.config.num_sample_frames_batch_size):
+            o, cache = self._encoder_pass(xt[s:e].contiguous(), cache)
+            outs.append(o)
+        return torch.cat(outs, dim=0)
+
+    @staticmethod
+    def _blend(a, b, extent, dim):
+        """blend_v / blend_h of the library on channels-last latent tiles [T, h, w, C] (bf16 roundings as in eager)."""
+        extent = min(a.shape[dim], b.shape[dim], extent)
+        for y in range(extent):
+            ia = [slice(None)] * 4
+            ib = [slice(None)] * 4
+            ia[dim] = a.shape[dim] - extent + y
+            ib[dim] = y
+            b[tuple(ib)] = a[tuple(ia)] * (1 - y / extent) + b[tuple(ib)] * (y / extent)
+        return b
+
+    # ------------------------------------------------------------------ public encode
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        """x [B, 3, T, H, W] -> AutoencoderKLOutput(latent_dist=DiagonalGaussianDistribution(moments [B, 2C, T', H/8, W/8]))."""
+        _lib.load()
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise RuntimeError("encode needs a CUDA tensor (no CPU fallback exists)")
+        c = self.config
+        if x.dim() != 5 or x.shape[1] != c.in_channels:
+            raise RuntimeError(f"x must be [B, {c.in_channels}, T, H, W]")
+        B, Cx, T, H, W = x.shape
+        if H % self.spatial_scale or W % self.spatial_scale:
+            raise RuntimeError(f"height and width must be multiples of {self.spatial_scale}")
+        th, tw = self.tile_sample_min_height, self.tile_sample_min_width
+        tiled = self.use_tiling and (W > tw or H > th)
+        moments = []
+        for b in range(B):
+            xcl = torch.zeros((T, H, W, self.cin_pad), dtype=BF16, device=self.device)
+            xcl[..., :Cx] = x[b].to(BF16).permute(1, 2, 3, 0)
+            if not tiled:
+                m = self._encode_tile(xcl)
+            else:
+                oh, ow = int(th * (1 - c.tile_overlap_factor_height)), int(tw * (1 - c.tile_overlap_factor_width))
+                bh = int(self.tile_latent_min_height * c.tile_overlap_factor_height)
+                bw = int(self.tile_latent_min_width * c.tile_overlap_factor_width)
+                lh, lw = self.tile_latent_min_height - bh, self.tile_latent_min_width - bw
+                rows = [[self._encode_tile(xcl[:, i:i + th, j:j + tw].contiguous()) for j in range(0, W, ow)]
+                        for i in range(0, H, oh)]
+                out_rows = []
+                for i, row in enumerate(rows):
+                    rr = []
+                    for j, tile in enumerate(row):
+                        if i > 0:
+                            tile = self._blend(rows[i - 1][j], tile, bh, 1)
+                        if j > 0:
+                            tile = self._blend(row[j - 1], tile, bw, 2)
+                        rr.append(tile[:, :lh, :lw])
+                    out_rows.append(torch.cat(rr, dim=2))
+                m = torch.cat(out_rows, dim=1)
+            moments.append(m.permute(3, 0, 1, 2))                          # [2C, T', h, w]
+        dist = DiagonalGaussianDistribution(torch.stack(moments, 0))
+        if not return_dict:
+            return (dist,)
+        return AutoencoderKLOutput(latent_dist=dist)
