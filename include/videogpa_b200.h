@@ -252,6 +252,21 @@ int vgpa_rmsnorm_rope_bf16(void* x, int rows, int D, int64_t ldx, const float* w
  * row stride lda, b fp32. */
 int vgpa_add_rows_bf16(const void* a, const float* b, void* out, int R, int64_t N, int64_t lda, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * T5 prompt encoder helpers. Replace transformers' T5Attention / T5DenseGatedActDense
+ * arithmetic behind `pipeline.text_encoder(input_ids)[0]` (train/CogVideoX-5B/02_encode.py:69-84, 226 tokens, no
+ * attention mask); the projections run on vgpa_linear_bf16 and T5LayerNorm on vgpa_rmsnorm_rope_bf16.
+ * ---------------------------------------------------------------------------------------------- */
+/* Self-attention with d_kv = 64, NO 1/sqrt(d) scaling and an additive position bias [H, S, S] (bf16):
+ * scores = bf16(q k^T); scores = bf16(scores + bias); P = bf16(softmax_fp32(scores)); out = bf16(P v).
+ * q, k, v: rows [B*S, ld_qkv] with head h at columns [64h, 64h+64) (pointers into a fused projection are fine);
+ * out [B*S, ldo]. 0 < S <= 512. */
+int vgpa_t5_attention_bf16(const void* q, const void* k, const void* v, const void* bias, void* out, int B, int H, int S,
+                           int64_t ld_qkv, int64_t ldo, void* stream);
+/* out = bf16(a * b) elementwise on [rows, N] (T5DenseGatedActDense: hidden_gelu * hidden_linear); N % 8 == 0. */
+int vgpa_gated_mul_bf16(const void* a, const void* b, void* out, int rows, int N, int64_t lda, int64_t ldb, int64_t ldo,
+                        void* stream);
+
 /* ================================================================================================
  * K4 — CogVideoX VAE decoder building blocks. Replace the cuDNN conv3d / GroupNorm / interpolate calls
  * behind diffusers' AutoencoderKLCogVideoX.decode (CogVideoXDecoder3D, CogVideoXResnetBlock3D,

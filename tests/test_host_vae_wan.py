@@ -110,3 +110,30 @@ def test_encoder_oracle_shapes_and_tiling_geometry():
     x17 = torch.cat([x, torch.rand(1, 3, 8, 16, 16, generator=torch.Generator().manual_seed(1))], dim=2)
     m17 = V.encode(sd, cfg, x17, tiling=False)
     assert m17.shape == (1, 32, 5, 2, 2) and torch.allclose(m17[:, :, :3], m, atol=1e-6)
+
+
+def test_t5_position_buckets_match_transformers():
+    """The relative-position bucket rule is integer work: bit-exact against transformers' own static method (the library the
+    reference's text_encoder comes from), for the encoder's bidirectional case at 226 and 512 tokens."""
+    from transformers.models.t5.modeling_t5 import T5Attention
+    from videogpa_b200.t5 import T5Config, position_buckets
+    for S in (1, 17, 226, 512):
+        ctx = torch.arange(S)[:, None]
+        mem = torch.arange(S)[None, :]
+        ref = T5Attention._relative_position_bucket(mem - ctx, bidirectional=True, num_buckets=32, max_distance=128)
+        got = position_buckets(S, 32, 128)
+        assert got.dtype == torch.long and torch.equal(got, ref)
+        assert int(got.min()) >= 0 and int(got.max()) < 32
+    c = T5Config()
+    assert (c.d_model, c.d_kv, c.num_heads, c.d_ff, c.num_layers) == (4096, 64, 64, 10240, 24)
+
+
+def test_t5_abi_argument_validation():
+    from videogpa_b200 import _lib
+    L = _lib.load()
+    assert L.vgpa_t5_attention_bf16(None, None, None, None, None, 1, 1, 8, 64, 64, None) != 0
+    assert b"null" in L.vgpa_last_error()
+    assert L.vgpa_t5_attention_bf16(16, 16, 16, 16, 16, 1, 1, 513, 64, 64, None) != 0 and b"512" in L.vgpa_last_error()
+    assert L.vgpa_t5_attention_bf16(16, 16, 16, 16, 16, 1, 2, 8, 64, 128, None) != 0
+    assert L.vgpa_gated_mul_bf16(16, 16, 16, 4, 12, 16, 16, 16, None) != 0 and b"multiple of 8" in L.vgpa_last_error()
+    assert L.vgpa_gated_mul_bf16(16, 16, 16, 4, 16, 8, 16, 16, None) != 0

@@ -147,6 +147,8 @@ SIGNATURES = {
     "vgpa_dpo_loss_backward": (c_int, [C.POINTER(DpoArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
     "vgpa_rmsnorm_rope_bf16": (c_int, [c_void_p, c_int, c_int, c_i64, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vgpa_add_rows_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p]),
+    "vgpa_t5_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_i64, c_void_p]),
+    "vgpa_gated_mul_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p]),
     "vgpa_conv3d_causal_bf16": (c_int, [C.POINTER(Conv3dArgs), c_void_p]),
     "vgpa_groupnorm_workspace_bytes": (C.c_size_t, [c_int]),
     "vgpa_groupnorm_stats_bf16": (c_int, [c_void_p, c_i64, c_int, c_int, c_float, c_void_p, C.c_size_t, c_void_p, c_void_p]),

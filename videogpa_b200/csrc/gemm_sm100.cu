@@ -392,7 +392,10 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
   VGPA_CHECK((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->W) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
              "vgpa_linear_bf16: pointers must be 16-byte aligned");
-  const int BN = (a->N % 256 == 0) ? 256 : 64;
+  int BN = (a->N % 256 == 0) ? 256 : 64;
+  // skinny problems (T5 prompt encoder: M = 226) are bound by streaming W once from HBM: with 128x256 tiles fewer CTAs
+  // than SMs would be pulling it, so use 128x64 tiles there
+  if (BN == 256 && static_cast<long long>((a->M + BM - 1) / BM) * (a->N / 256) < 148) BN = 64;
   // cluster of 2 with W-tile multicast for the big GEMMs (development knob VGPA_GEMM_CLUSTER=0 turns it off)
   static int use_cluster = -1;
   if (use_cluster < 0) {

@@ -4,7 +4,8 @@ Mirrors the tensor half of `encode_video_latent` (`train/CogVideoX-5B/02_encode.
 `train/CogVideoX1.5-5B/02_encode.py:100-121`): sample a fixed number of frames, scale uint8 frames to [0, 1] (the reference
 does NOT map them to [-1, 1]), `vae.encode(video).latent_dist.sample()`, move the latent to the host. The 5B scripts store
 the latent unscaled, the 1.5 script multiplies by `vae.config.scaling_factor` — both kept, chosen by `scale_latents`.
-Video decoding (decord) and the T5 prompt encoder are outside this build: callers pass the decoded frames.
+`encode_text_condition` mirrors `encode_text_condition` of the same script (:69-93) on videogpa_b200.t5.T5EncoderModel.
+Video decoding (decord) is outside this build: callers pass the decoded frames.
 """
 from __future__ import annotations
 
@@ -38,3 +39,13 @@ def encode_video_latent(vae_encoder, frames, num_frames: int = 49, scale_latents
     if scale_latents:
         latent = latent * vae_encoder.config.scaling_factor
     return latent.squeeze(0).cpu()
+
+
+@torch.no_grad()
+def encode_text_condition(text_encoder, input_ids: torch.Tensor) -> dict:
+    """`encode_text_condition` (train/CogVideoX-5B/02_encode.py:69-93) after tokenisation: ids [1, 226] (max-length padded,
+    truncated) -> {"encoder_hidden_states": [226, d_model] on the host}, the dict the script saves as `cond_<group>.pt`."""
+    if input_ids.dim() != 2 or input_ids.shape[0] != 1:
+        raise RuntimeError("input_ids must be [1, S]")
+    emb = text_encoder(input_ids.to(text_encoder.device))[0].squeeze(0).cpu()
+    return {"encoder_hidden_states": emb}

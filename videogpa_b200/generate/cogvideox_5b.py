@@ -72,10 +72,19 @@ def _load_safetensors_dir(d: Path) -> dict:
 
 
 class _T5Prompts:
+    """`encode_prompt` of the diffusers pipeline: tokenizer (transformers, host string work) + the T5 encoder on the
+    sm_100a kernels (videogpa_b200.t5), 226 max-length-padded tokens, no attention mask."""
+
     def __init__(self, base: Path, device):
-        from transformers import AutoTokenizer, T5EncoderModel
+        from transformers import AutoTokenizer
+        from ..t5 import T5Config, T5EncoderModel
         self.tok = AutoTokenizer.from_pretrained(str(base / "tokenizer"))
-        self.enc = T5EncoderModel.from_pretrained(str(base / "text_encoder"), torch_dtype=torch.bfloat16).to(device).eval()
+        tcfg = json.loads((base / "text_encoder" / "config.json").read_text())
+        if tcfg.get("feed_forward_proj", "gated-gelu") != "gated-gelu":
+            raise RuntimeError("only the gated-gelu T5 v1.1 text encoder is supported")
+        known = T5Config.__dataclass_fields__.keys()
+        self.enc = T5EncoderModel(T5Config(**{k: v for k, v in tcfg.items() if k in known}),
+                                  _load_safetensors_dir(base / "text_encoder"), device=device)
         self.device = device
 
     @torch.no_grad()
