@@ -326,6 +326,40 @@ def run_ours(args, rank, world, local):
     except Exception as ex:
         vae = {"error": str(ex)}
 
+    # ---- the encoders either side of the path: VAE encode of a 49-frame clip, T5-XXL prompt encode
+    enc_leg = None
+    try:
+        from videogpa_b200.t5 import T5Config, T5EncoderModel
+        from videogpa_b200.vae import AutoencoderKLCogVideoXEncoder
+        ve = AutoencoderKLCogVideoXEncoder.random_init(VAEDecoderConfig(), seed=6, device=dev)
+        ve.enable_tiling(); ve.enable_slicing()
+        clip = (torch.rand(1, 3, 49, 480, 720, device=dev, generator=torch.Generator(device=dev).manual_seed(3)) * 2 - 1).to(torch.bfloat16)
+        ve.encode(clip)
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(2):
+            mom = ve.encode(clip).latent_dist.parameters
+        v1.record(); torch.cuda.synchronize()
+        enc_ms = v0.elapsed_time(v1) / 2
+        del ve, clip
+        t5 = T5EncoderModel.random_init(T5Config(), seed=3, device=dev)
+        ids = torch.randint(0, 32128, (1, 226), device=dev, generator=torch.Generator(device=dev).manual_seed(4))
+        t5(ids); t5(ids)                                          # eager pass + capture, first replay
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(5):
+            emb = t5(ids)[0]
+        v1.record(); torch.cuda.synchronize()
+        t5_ms = v0.elapsed_time(v1) / 5
+        enc_leg = {"vae_encode_ms_per_clip": enc_ms, "vae_encode_workload": "49f 480x720, tiled 3x3, passes of 9 + 5 x 8 frames",
+                   "moments": list(mom.shape), "t5_xxl_ms_per_prompt": t5_ms, "t5_workload": "24 layers, d_model 4096, 226 tokens, no mask",
+                   "t5_weight_gbs": 24 * (4 * 4096 * 4096 + 3 * 4096 * 10240) * 2 / (t5_ms / 1000.0) / 1e9,
+                   "finite": bool(torch.isfinite(mom.float()).all().item() and torch.isfinite(emb.float()).all().item()),
+                   "weights": "random-init"}
+        del t5, emb, mom
+    except Exception as ex:
+        enc_leg = {"error": str(ex)}
+
     # ---- Wan2.2-TI2V-5B guided denoise step (BASELINE.json configs[3] shapes: 81 frames 1280x704, S = 18 480), reported beside
     wan = None
     try:
@@ -373,7 +407,7 @@ def run_ours(args, rank, world, local):
                      "flops_per_launch": attn_flops, "avg_launch_ms": attn_avg_ms, "launches_timed": len(attn_ms),
                      "share_of_step": (sum(attn_ms) / ms_max) if ms_max > 0 else None},
         "step_tflops": step_flops * args.steps / (ms_max / 1000.0) / 1e12, "kernel_families": families,
-        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae, "wan_step": wan,
+        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae, "encoders": enc_leg, "wan_step": wan,
     }
     print(json.dumps(line), flush=True)
 
