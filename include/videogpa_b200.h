@@ -95,9 +95,38 @@ typedef struct vgpa_attention_args {
   float scale;     /* softmax scale; <= 0 means 1/sqrt(head_dim) */
   int64_t q_row_stride, k_row_stride, v_row_stride, out_row_stride;         /* elements */
   int64_t q_batch_stride, k_batch_stride, v_batch_stride, out_batch_stride; /* elements */
+  float* lse;      /* optional [B, H, Sq] fp32: log2-domain logsumexp of the scaled scores, saved for
+                      vgpa_attention_bwd_bf16 (head_dim 64 only); NULL = not written */
 } vgpa_attention_args;
 
 int vgpa_attention_bf16(const vgpa_attention_args* args, void* stream);
+
+/* Backward of vgpa_attention_bf16 (head_dim 64) — the DPO training step differentiates through
+ * F.scaled_dot_product_attention (train/CogVideoX-5B/03_train.py:134-157).
+ * Given q, k, v, the forward output `out`, its logsumexp `lse` (written by the forward call) and d_out:
+ *   P = exp2(scale*log2e * q k^T - lse),  delta = rowsum(d_out * out),  dS = P * (d_out v^T - delta) * scale,
+ *   dq = dS k,  dk = dS^T q,  dv = P^T d_out      (bf16 outputs, fp32 accumulation, deterministic).
+ * workspace: vgpa_attention_bwd_workspace_bytes(B, H, Sq) bytes of device scratch (delta). */
+typedef struct vgpa_attention_bwd_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* out;    /* forward output [B, Sq, >=H*64] */
+  const void* d_out;  /* gradient of the output, same shape */
+  const float* lse;   /* [B, H, Sq] from the forward call */
+  void* dq;           /* [B, Sq,  >=H*64] bf16 */
+  void* dk;           /* [B, Skv, >=H*64] bf16 */
+  void* dv;           /* [B, Skv, >=H*64] bf16 */
+  int32_t B, H, Sq, Skv, head_dim;
+  float scale;
+  int64_t q_row_stride, k_row_stride, v_row_stride, out_row_stride, dout_row_stride, dq_row_stride, dk_row_stride, dv_row_stride;
+  int64_t q_batch_stride, k_batch_stride, v_batch_stride, out_batch_stride, dout_batch_stride, dq_batch_stride,
+      dk_batch_stride, dv_batch_stride;
+  void* workspace;
+  size_t workspace_bytes;
+} vgpa_attention_bwd_args;
+size_t vgpa_attention_bwd_workspace_bytes(int B, int H, int Sq);
+int vgpa_attention_bwd_bf16(const vgpa_attention_bwd_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3 — fused LayerNorm + adaLN modulation: out = LN(x) * (1 + scale[b, seg]) + shift[b, seg].

@@ -42,6 +42,21 @@ class AttentionArgs(C.Structure):
         ("scale", c_float),
         ("q_row_stride", c_i64), ("k_row_stride", c_i64), ("v_row_stride", c_i64), ("out_row_stride", c_i64),
         ("q_batch_stride", c_i64), ("k_batch_stride", c_i64), ("v_batch_stride", c_i64), ("out_batch_stride", c_i64),
+        ("lse", c_void_p),
+    ]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("out", c_void_p), ("d_out", c_void_p), ("lse", c_void_p),
+        ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
+        ("B", c_i32), ("H", c_i32), ("Sq", c_i32), ("Skv", c_i32), ("head_dim", c_i32),
+        ("scale", c_float),
+        ("q_row_stride", c_i64), ("k_row_stride", c_i64), ("v_row_stride", c_i64), ("out_row_stride", c_i64),
+        ("dout_row_stride", c_i64), ("dq_row_stride", c_i64), ("dk_row_stride", c_i64), ("dv_row_stride", c_i64),
+        ("q_batch_stride", c_i64), ("k_batch_stride", c_i64), ("v_batch_stride", c_i64), ("out_batch_stride", c_i64),
+        ("dout_batch_stride", c_i64), ("dq_batch_stride", c_i64), ("dk_batch_stride", c_i64), ("dv_batch_stride", c_i64),
+        ("workspace", c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -120,6 +135,8 @@ SIGNATURES = {
     "vgpa_device_sm_count": (c_int, []),
     "vgpa_linear_bf16": (c_int, [C.POINTER(LinearArgs), c_void_p]),
     "vgpa_attention_bf16": (c_int, [C.POINTER(AttentionArgs), c_void_p]),
+    "vgpa_attention_bwd_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
+    "vgpa_attention_bwd_bf16": (c_int, [C.POINTER(AttentionBwdArgs), c_void_p]),
     "vgpa_layernorm_modulate_bf16": (c_int, [C.POINTER(LayerNormArgs), c_void_p]),
     "vgpa_linear_smallm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_i64, c_int, c_void_p]),
     "vgpa_timestep_embedding_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

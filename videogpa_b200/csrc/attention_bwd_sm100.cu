@@ -1,0 +1,460 @@
+// K2b: attention backward for head_dim 64 on tcgen05 — SURVEY.md §8 row f-2 (the DPO training step differentiates
+// through F.scaled_dot_product_attention inside CogVideoXAttnProcessor2_0; train/CogVideoX-5B/03_train.py:134-157).
+//
+// Recompute form (no S x S tensor in HBM): the forward saves the log2-domain logsumexp L of every row; with
+// delta = rowsum(dO * O),  P = exp2(scale_log2 * q k^T - L),  dS = P * (dP - delta) * scale,  dP = dO v^T:
+//     dQ = dS k        dK = dS^T q        dV = P^T dO
+// Two kernels, so that no output needs atomics (results are deterministic):
+//   * attn_bwd_dq_kernel:  one CTA per (128-query tile, head, sample), loops over kv tiles.
+//       S = Q K^T and dP = dO V^T (SS MMAs, N = 128) -> TMEM; 128 threads (one per query row) turn them into dS (bf16,
+//       back into TMEM); dQ += dS K_j is a TS MMA whose B operand is the SAME K tile read MN-major.
+//   * attn_bwd_dkv_kernel: one CTA per (128-key tile, head, sample), loops over query tiles, transposed problem:
+//       S^T = K Q^T, dP^T = V dO^T -> TMEM; threads own key rows, L / delta of the 128 queries come from shared memory;
+//       dV += P^T dO_i and dK += dS^T Q_i are TS MMAs with the dO / Q tiles read MN-major.
+// TMEM: dq kernel 384 columns (S 128, dP 128, dS 64, dQ 64); dkv kernel 512 (S^T, dP^T 128 each; P^T, dS^T, dV, dK 64 each).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (elect.sync), warps 2-5 compute. First version: the MMA and the
+// compute phase of one tile alternate (single-buffered S / dP), so the tensor pipe idles while dS is computed.
+#include "sm100.cuh"
+#include "../../include/videogpa_b200.h"
+#include <math.h>
+
+namespace vgpa {
+namespace {
+
+constexpr int AB_THREADS = 192;
+constexpr int AB_T = 128;                                   // tile rows (queries or keys)
+constexpr int AB_D = 64;
+constexpr uint32_t AB_TILE = AB_T * AB_D * 2;               // 16384 bytes
+constexpr uint32_t AB_SMEM_DQ = 2 * AB_TILE + 2 * 2 * AB_TILE + 1024 + 256;            // Q, dO + 2 x (K, V)
+constexpr uint32_t AB_SMEM_DKV = 2 * AB_TILE + 2 * 2 * AB_TILE + 2 * 2 * AB_T * 4 + 1024 + 256;   // K, V + 2 x (Q, dO) + L/delta
+
+struct BwdParams {
+  const float* lse;        // [B, H, Sq]
+  const float* delta;      // [B, H, Sq]
+  __nv_bfloat16* dq;
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+  long long dq_row_stride, dq_batch_stride, dk_row_stride, dk_batch_stride, dv_row_stride, dv_batch_stride;
+  int Sq, Skv, H;
+  float scale, scale_log2;
+};
+
+__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, uint32_t tmem_addr) {
+#pragma unroll
+  for (int c = 0; c < AB_D / 16; ++c) {
+    uint32_t o[16];
+    ptx::tmem_ld_32x16(tmem_addr + c * 16, o);
+    ptx::tmem_ld_wait();
+    if (dst != nullptr) {
+      uint4 v0, v1;
+      v0.x = pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1]));
+      v0.y = pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3]));
+      v0.z = pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5]));
+      v0.w = pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7]));
+      v1.x = pack_bf16x2(__uint_as_float(o[8]), __uint_as_float(o[9]));
+      v1.y = pack_bf16x2(__uint_as_float(o[10]), __uint_as_float(o[11]));
+      v1.z = pack_bf16x2(__uint_as_float(o[12]), __uint_as_float(o[13]));
+      v1.w = pack_bf16x2(__uint_as_float(o[14]), __uint_as_float(o[15]));
+      reinterpret_cast<uint4*>(dst + c * 16)[0] = v0;
+      reinterpret_cast<uint4*>(dst + c * 16)[1] = v1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dQ
+constexpr uint32_t DQ_COL_S = 0, DQ_COL_DP = 128, DQ_COL_DS = 256, DQ_COL_DQ = 320, DQ_TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, BwdParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + AB_TILE;
+  uint8_t* sKV = sdO + AB_TILE;                         // slot s: K at s * 2 tiles, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 4 * AB_TILE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                         // [2]
+  uint64_t* kv_empty = bars + 3;                        // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* dq_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int m0 = blockIdx.x * AB_T;
+  const int nkv = (prm.Skv + AB_T - 1) / AB_T;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
+    ptx::mbar_init(sdp_full, 1);
+    ptx::mbar_init(ds_ready, 128);
+    ptx::mbar_init(dq_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, DQ_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(q_full, 2 * AB_TILE);
+      ptx::tma_load_3d(sQ, &tmQ, q_full, head * AB_D, m0, batch);
+      ptx::tma_load_3d(sdO, &tmdO, q_full, head * AB_D, m0, batch);
+      for (int j = 0; j < nkv; ++j) {
+        const int slot = j & 1;
+        ptx::mbar_wait(&kv_empty[slot], ((j >> 1) & 1) ^ 1);
+        ptx::mbar_expect_tx(&kv_full[slot], 2 * AB_TILE);
+        ptx::tma_load_3d(sKV + slot * 2 * AB_TILE, &tmK, &kv_full[slot], head * AB_D, j * AB_T, batch);
+        ptx::tma_load_3d(sKV + slot * 2 * AB_TILE + AB_TILE, &tmV, &kv_full[slot], head * AB_D, j * AB_T, batch);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = ptx::idesc_bf16(AB_T, AB_T, 0, 0);     // [128 x 64] x [128 x 64]^T, both K-major
+    constexpr uint32_t idesc_o = ptx::idesc_bf16(AB_T, AB_D, 0, 1);     // TMEM [128 x 128] x tile [128 x 64] read MN-major
+    const uint32_t sQ_a = ptx::smem_u32(sQ), sdO_a = ptx::smem_u32(sdO), sKV_a = ptx::smem_u32(sKV);
+    if (ptx::elect_one()) {
+      ptx::mbar_wait(q_full, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int slot = j & 1;
+        const uint32_t sK_a = sKV_a + slot * 2 * AB_TILE, sV_a = sK_a + AB_TILE;
+        ptx::mbar_wait(&kv_full[slot], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        {
+          const uint64_t a = ptx::smem_desc_sw128(sQ_a, 16, 1024), b = ptx::smem_desc_sw128(sK_a, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + DQ_COL_S, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        {
+          const uint64_t a = ptx::smem_desc_sw128(sdO_a, 16, 1024), b = ptx::smem_desc_sw128(sV_a, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + DQ_COL_DP, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(sdp_full);
+        ptx::mbar_wait(ds_ready, j & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < AB_T / 16; ++kk) {
+          const uint64_t b = ptx::smem_desc_sw128(sK_a + kk * 2048, 1024, 1024);
+          ptx::umma_ts(tmem_base + DQ_COL_DQ, tmem_base + DQ_COL_DS + kk * 8, b, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&kv_empty[slot]);
+      }
+      ptx::umma_commit(dq_done);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int row = m0 + r;
+    const bool live = row < prm.Sq;
+    const long long stat = (static_cast<long long>(batch) * prm.H + head) * prm.Sq + (live ? row : 0);
+    const float L = live ? prm.lse[stat] : INFINITY;          // rows past the end get P = 0
+    const float dl = live ? prm.delta[stat] : 0.f;
+    const float sc = prm.scale_log2, scale = prm.scale;
+    const int tail = prm.Skv - (nkv - 1) * AB_T;
+    for (int j = 0; j < nkv; ++j) {
+      ptx::mbar_wait(sdp_full, j & 1);
+      ptx::tc_fence_after();
+      const int valid = (j == nkv - 1) ? tail : AB_T;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], dp[32], pk[16];
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_S + c * 32, s);
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_DP + c * 32, dp);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float d0, d1;
+          {
+            const float p = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * i]), sc, -L));
+            d0 = (c * 32 + 2 * i < valid) ? p * (__uint_as_float(dp[2 * i]) - dl) * scale : 0.f;
+          }
+          {
+            const float p = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sc, -L));
+            d1 = (c * 32 + 2 * i + 1 < valid) ? p * (__uint_as_float(dp[2 * i + 1]) - dl) * scale : 0.f;
+          }
+          pk[i] = pack_bf16x2(d0, d1);
+        }
+        ptx::tmem_st_32x16(tmem_base + lane_addr + DQ_COL_DS + c * 16, pk);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(ds_ready);
+    }
+    ptx::mbar_wait(dq_done, 0);
+    ptx::tc_fence_after();
+    __nv_bfloat16* dst = live ? prm.dq + static_cast<long long>(batch) * prm.dq_batch_stride +
+                                    static_cast<long long>(row) * prm.dq_row_stride + head * AB_D
+                              : nullptr;
+    store_row64(dst, tmem_base + lane_addr + DQ_COL_DQ);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, DQ_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ dK, dV
+constexpr uint32_t KV_COL_ST = 0, KV_COL_DPT = 128, KV_COL_PT = 256, KV_COL_DST = 320, KV_COL_DV = 384, KV_COL_DK = 448,
+                   KV_TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, BwdParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + AB_TILE;
+  uint8_t* sQdO = sV + AB_TILE;                         // slot s: Q at s * 2 tiles, dO right after
+  float* sL = reinterpret_cast<float*>(sQdO + 4 * AB_TILE);     // [2][128]
+  float* sDl = sL + 2 * AB_T;                                    // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * AB_T);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;                          // [2]
+  uint64_t* q_empty = bars + 3;                         // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* acc_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int n0 = blockIdx.x * AB_T;
+  const int nq = (prm.Sq + AB_T - 1) / AB_T;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
+    ptx::mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 1); }
+    ptx::mbar_init(sdp_full, 1);
+    ptx::mbar_init(ds_ready, 128);
+    ptx::mbar_init(acc_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, KV_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(kv_full, 2 * AB_TILE);
+      ptx::tma_load_3d(sK, &tmK, kv_full, head * AB_D, n0, batch);
+      ptx::tma_load_3d(sV, &tmV, kv_full, head * AB_D, n0, batch);
+      for (int i = 0; i < nq; ++i) {
+        const int slot = i & 1;
+        ptx::mbar_wait(&q_empty[slot], ((i >> 1) & 1) ^ 1);
+        ptx::mbar_expect_tx(&q_full[slot], 2 * AB_TILE);
+        ptx::tma_load_3d(sQdO + slot * 2 * AB_TILE, &tmQ, &q_full[slot], head * AB_D, i * AB_T, batch);
+        ptx::tma_load_3d(sQdO + slot * 2 * AB_TILE + AB_TILE, &tmdO, &q_full[slot], head * AB_D, i * AB_T, batch);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = ptx::idesc_bf16(AB_T, AB_T, 0, 0);
+    constexpr uint32_t idesc_o = ptx::idesc_bf16(AB_T, AB_D, 0, 1);
+    const uint32_t sK_a = ptx::smem_u32(sK), sV_a = ptx::smem_u32(sV), sQdO_a = ptx::smem_u32(sQdO);
+    if (ptx::elect_one()) {
+      ptx::mbar_wait(kv_full, 0);
+      for (int i = 0; i < nq; ++i) {
+        const int slot = i & 1;
+        const uint32_t sQ_a = sQdO_a + slot * 2 * AB_TILE, sdO_a = sQ_a + AB_TILE;
+        ptx::mbar_wait(&q_full[slot], (i >> 1) & 1);
+        ptx::tc_fence_after();
+        {
+          const uint64_t a = ptx::smem_desc_sw128(sK_a, 16, 1024), b = ptx::smem_desc_sw128(sQ_a, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + KV_COL_ST, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        {
+          const uint64_t a = ptx::smem_desc_sw128(sV_a, 16, 1024), b = ptx::smem_desc_sw128(sdO_a, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + KV_COL_DPT, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(sdp_full);
+        ptx::mbar_wait(ds_ready, i & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < AB_T / 16; ++kk) {
+          const uint64_t b = ptx::smem_desc_sw128(sdO_a + kk * 2048, 1024, 1024);
+          ptx::umma_ts(tmem_base + KV_COL_DV, tmem_base + KV_COL_PT + kk * 8, b, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < AB_T / 16; ++kk) {
+          const uint64_t b = ptx::smem_desc_sw128(sQ_a + kk * 2048, 1024, 1024);
+          ptx::umma_ts(tmem_base + KV_COL_DK, tmem_base + KV_COL_DST + kk * 8, b, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&q_empty[slot]);
+      }
+      ptx::umma_commit(acc_done);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                    // key row inside the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const long long stat0 = (static_cast<long long>(batch) * prm.H + head) * prm.Sq;
+    const float sc = prm.scale_log2, scale = prm.scale;
+    for (int i = 0; i < nq; ++i) {
+      const int slot = i & 1;
+      {
+        const int q = i * AB_T + r;
+        const bool ok = q < prm.Sq;
+        sL[slot * AB_T + r] = ok ? prm.lse[stat0 + q] : INFINITY;      // queries past the end: P = 0
+        sDl[slot * AB_T + r] = ok ? prm.delta[stat0 + q] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      ptx::mbar_wait(sdp_full, i & 1);
+      ptx::tc_fence_after();
+      const float* Lq = sL + slot * AB_T;
+      const float* Dq = sDl + slot * AB_T;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], dp[32], pp[16], pd[16];
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_ST + c * 32, s);
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_DPT + c * 32, dp);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int q0 = c * 32 + 2 * k;
+          const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * k]), sc, -Lq[q0]));
+          const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * k + 1]), sc, -Lq[q0 + 1]));
+          const float d0 = p0 * (__uint_as_float(dp[2 * k]) - Dq[q0]) * scale;
+          const float d1 = p1 * (__uint_as_float(dp[2 * k + 1]) - Dq[q0 + 1]) * scale;
+          pp[k] = pack_bf16x2(p0, p1);
+          pd[k] = pack_bf16x2(d0, d1);
+        }
+        ptx::tmem_st_32x16(tmem_base + lane_addr + KV_COL_PT + c * 16, pp);
+        ptx::tmem_st_32x16(tmem_base + lane_addr + KV_COL_DST + c * 16, pd);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(ds_ready);
+    }
+    ptx::mbar_wait(acc_done, 0);
+    ptx::tc_fence_after();
+    const int row = n0 + r;
+    const bool live = row < prm.Skv;
+    __nv_bfloat16* dvp = live ? prm.dv + static_cast<long long>(batch) * prm.dv_batch_stride +
+                                    static_cast<long long>(row) * prm.dv_row_stride + head * AB_D : nullptr;
+    __nv_bfloat16* dkp = live ? prm.dk + static_cast<long long>(batch) * prm.dk_batch_stride +
+                                    static_cast<long long>(row) * prm.dk_row_stride + head * AB_D : nullptr;
+    store_row64(dvp, tmem_base + lane_addr + KV_COL_DV);
+    store_row64(dkp, tmem_base + lane_addr + KV_COL_DK);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, KV_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ delta = rowsum(dO * O)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                  int B, int H, int S, long long o_row, long long o_batch, long long do_row, long long do_batch) {
+  const long long total = static_cast<long long>(B) * H * S;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i % S);
+    const int h = static_cast<int>((i / S) % H);
+    const int b = static_cast<int>(i / (static_cast<long long>(S) * H));
+    const uint4* po = reinterpret_cast<const uint4*>(o + b * o_batch + s * o_row + h * AB_D);
+    const uint4* pd = reinterpret_cast<const uint4*>(d_o + b * do_batch + s * do_row + h * AB_D);
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const uint4 a = __ldg(po + v), g = __ldg(pd + v);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 af = unpack_bf16x2(aw[k]), gf = unpack_bf16x2(gw[k]);
+        acc = fmaf(af.x, gf.x, acc);
+        acc = fmaf(af.y, gf.y, acc);
+      }
+    }
+    delta[i] = acc;                                       // layout [B, H, S]
+  }
+}
+
+}  // namespace
+}  // namespace vgpa
+
+extern "C" size_t vgpa_attention_bwd_workspace_bytes(int B, int H, int Sq) {
+  return static_cast<size_t>(B) * H * Sq * sizeof(float);
+}
+
+extern "C" int vgpa_attention_bwd_bf16(const vgpa_attention_bwd_args* a, void* stream) {
+  using namespace vgpa;
+  VGPA_CHECK(a != nullptr, "vgpa_attention_bwd_bf16: null args");
+  VGPA_CHECK(a->head_dim == 64, "vgpa_attention_bwd_bf16: head_dim must be 64 (got %d)", a->head_dim);
+  VGPA_CHECK(a->B > 0 && a->H > 0 && a->Sq > 0 && a->Skv > 0, "vgpa_attention_bwd_bf16: bad shape B=%d H=%d Sq=%d Skv=%d", a->B, a->H, a->Sq, a->Skv);
+  VGPA_CHECK(a->q && a->k && a->v && a->out && a->d_out && a->lse && a->dq && a->dk && a->dv, "vgpa_attention_bwd_bf16: null tensor pointer");
+  VGPA_CHECK(a->workspace != nullptr && a->workspace_bytes >= vgpa_attention_bwd_workspace_bytes(a->B, a->H, a->Sq),
+             "vgpa_attention_bwd_bf16: workspace too small (%zu bytes needed)", vgpa_attention_bwd_workspace_bytes(a->B, a->H, a->Sq));
+  const int cols = a->H * 64;
+  const int64_t strides[] = {a->q_row_stride, a->k_row_stride, a->v_row_stride, a->out_row_stride, a->dout_row_stride,
+                             a->dq_row_stride, a->dk_row_stride, a->dv_row_stride};
+  for (int64_t st : strides) VGPA_CHECK(st % 8 == 0 && st >= cols, "vgpa_attention_bwd_bf16: row strides must be multiples of 8 covering H*64 columns");
+  const int64_t bstr[] = {a->q_batch_stride, a->k_batch_stride, a->v_batch_stride, a->out_batch_stride, a->dout_batch_stride,
+                          a->dq_batch_stride, a->dk_batch_stride, a->dv_batch_stride};
+  for (int64_t st : bstr) VGPA_CHECK(st % 8 == 0, "vgpa_attention_bwd_bf16: batch strides must be multiples of 8 elements");
+  VGPA_CHECK(((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
+               reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->d_out) | reinterpret_cast<uintptr_t>(a->dq) |
+               reinterpret_cast<uintptr_t>(a->dk) | reinterpret_cast<uintptr_t>(a->dv)) & 15) == 0,
+             "vgpa_attention_bwd_bf16: pointers must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* delta = static_cast<float*>(a->workspace);
+  {
+    const long long total = static_cast<long long>(a->B) * a->H * a->Sq;
+    long long grid = (total + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    attn_delta_kernel<<<static_cast<unsigned>(grid), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(a->out), static_cast<const __nv_bfloat16*>(a->d_out), delta, a->B, a->H, a->Sq,
+        a->out_row_stride, a->out_batch_stride, a->dout_row_stride, a->dout_batch_stride);
+    VGPA_LAUNCH_CHECK("attn_delta_kernel");
+  }
+  CUtensorMap tq, tk, tv, tdo;
+  const uint32_t box[3] = {64, 128, 1};
+  auto mk = [&](CUtensorMap* tm, const void* p, int S, int64_t row, int64_t batch) {
+    const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)S, (uint64_t)a->B};
+    const uint64_t str[2] = {(uint64_t)row * 2, (uint64_t)batch * 2};
+    return make_tmap_bf16(tm, p, 3, dims, str, box);
+  };
+  if (int rc = mk(&tq, a->q, a->Sq, a->q_row_stride, a->q_batch_stride)) return rc;
+  if (int rc = mk(&tk, a->k, a->Skv, a->k_row_stride, a->k_batch_stride)) return rc;
+  if (int rc = mk(&tv, a->v, a->Skv, a->v_row_stride, a->v_batch_stride)) return rc;
+  if (int rc = mk(&tdo, a->d_out, a->Sq, a->dout_row_stride, a->dout_batch_stride)) return rc;
+  BwdParams prm;
+  prm.lse = a->lse; prm.delta = delta;
+  prm.dq = static_cast<__nv_bfloat16*>(a->dq); prm.dk = static_cast<__nv_bfloat16*>(a->dk); prm.dv = static_cast<__nv_bfloat16*>(a->dv);
+  prm.dq_row_stride = a->dq_row_stride; prm.dq_batch_stride = a->dq_batch_stride;
+  prm.dk_row_stride = a->dk_row_stride; prm.dk_batch_stride = a->dk_batch_stride;
+  prm.dv_row_stride = a->dv_row_stride; prm.dv_batch_stride = a->dv_batch_stride;
+  prm.Sq = a->Sq; prm.Skv = a->Skv; prm.H = a->H;
+  prm.scale = a->scale > 0.f ? a->scale : 0.125f;
+  prm.scale_log2 = prm.scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VGPA_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_DQ));
+    VGPA_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_DKV));
+    attr_set = true;
+  }
+  attn_bwd_dq_kernel<<<dim3((a->Sq + AB_T - 1) / AB_T, a->H, a->B), AB_THREADS, AB_SMEM_DQ, s>>>(tq, tk, tv, tdo, prm);
+  VGPA_LAUNCH_CHECK("attn_bwd_dq_kernel");
+  attn_bwd_dkv_kernel<<<dim3((a->Skv + AB_T - 1) / AB_T, a->H, a->B), AB_THREADS, AB_SMEM_DKV, s>>>(tq, tk, tv, tdo, prm);
+  VGPA_LAUNCH_CHECK("attn_bwd_dkv_kernel");
+  return 0;
+}

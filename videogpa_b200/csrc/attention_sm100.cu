@@ -57,6 +57,8 @@ struct AttnParams {
   long long out_batch_stride;
   int Sq, Skv;
   float scale_log2;
+  float* lse;          // optional [B, H, Sq]: log2-domain logsumexp of the scaled scores (for the backward kernels)
+  int H;
 };
 
 using namespace attn;
@@ -382,6 +384,8 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float l = (la + lb) + (lc + ld);
     const int row = m0 + t * AT_BM + r;
     const float inv_l = 1.0f / l;
+    if (prm.lse != nullptr && row < prm.Sq)
+      prm.lse[(static_cast<long long>(batch) * prm.H + head) * prm.Sq + row] = m_used + log2f(l);
     __nv_bfloat16* orow = prm.out + static_cast<long long>(batch) * prm.out_batch_stride +
                           static_cast<long long>(row < prm.Sq ? row : 0) * prm.out_row_stride + head * AT_D;
 #pragma unroll
@@ -449,6 +453,7 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
   const int cols = a->H * a->head_dim;
   VGPA_CHECK(a->q_row_stride >= cols && a->k_row_stride >= cols && a->v_row_stride >= cols && a->out_row_stride >= cols,
              "vgpa_attention_bf16: row strides must cover H*head_dim columns");
+  VGPA_CHECK(a->lse == nullptr || a->head_dim == 64, "vgpa_attention_bf16: the logsumexp output is only available for head_dim 64");
   if (a->head_dim == 128) return launch_attention_d128(a, static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tk, tv;
   const uint32_t box[3] = {64, 128, 1};
@@ -473,6 +478,8 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
   prm.out_batch_stride = a->out_batch_stride;
   prm.Sq = a->Sq;
   prm.Skv = a->Skv;
+  prm.lse = a->lse;
+  prm.H = a->H;
   const float scale = a->scale > 0.f ? a->scale : 0.125f;
   prm.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((a->Sq + 2 * AT_BM - 1) / (2 * AT_BM), a->H, a->B);
@@ -489,7 +496,7 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
     const char* e = getenv("VGPA_ATTN_X4");
     x4 = e ? atoi(e) : 0;
   }
-  if (x4) return launch_attention_d64x4(tq, tk, tv, a, npoly, s);
+  if (x4 && a->lse == nullptr) return launch_attention_d64x4(tq, tk, tv, a, npoly, s);
   switch (npoly) {
     case 0: return launch_attn<0>(tq, tk, tv, prm, grid, s);
     case 32: return launch_attn<32>(tq, tk, tv, prm, grid, s);

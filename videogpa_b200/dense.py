@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_SILU, EPI_ACCUM, EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV,
+from ._lib import (AttentionBwdArgs, ACT_NONE, ACT_SILU, EPI_ACCUM, EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV,
                    SCHED_DDIM, SCHED_DPM, AttentionArgs, LayerNormArgs, LinearArgs, SchedArgs)
 
 BF16 = torch.bfloat16
@@ -82,7 +82,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
-              out: torch.Tensor | None = None, scale: float = 0.0, head_dim: int = 64) -> torch.Tensor:
+              out: torch.Tensor | None = None, scale: float = 0.0, head_dim: int = 64,
+              lse: torch.Tensor | None = None) -> torch.Tensor:
     """softmax(q k^T * scale) v with heads packed along the last dim.
 
     q: [B, Sq, >=heads*64] view, k/v: [B, Skv, >=heads*64] views (last dim contiguous; they may be
@@ -104,8 +105,44 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
     a.scale = scale
     a.q_row_stride, a.k_row_stride, a.v_row_stride, a.out_row_stride = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
     a.q_batch_stride, a.k_batch_stride, a.v_batch_stride, a.out_batch_stride = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    if lse is not None:                                   # [B, heads, Sq] fp32, saved for attention_backward
+        _req(lse, torch.float32, "lse")
+        if tuple(lse.shape) != (B, heads, Sq):
+            raise RuntimeError(f"attention: lse must be [{B}, {heads}, {Sq}]")
+        a.lse = lse.data_ptr()
     _lib.check(lib.vgpa_attention_bf16(C.byref(a), _lib.current_stream()), "vgpa_attention_bf16")
     return out
+
+
+def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor,
+                       lse: torch.Tensor, heads: int, *, scale: float = 0.0):
+    """(dq, dk, dv) of `attention` (head_dim 64) from the saved output and logsumexp; see vgpa_attention_bwd_bf16."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (d_out, "d_out")):
+        _req(t, BF16, n, contiguous=False)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise RuntimeError(f"attention_backward: {n} must be [B, S, cols] with a contiguous last dimension")
+    _req(lse, torch.float32, "lse")
+    B, Sq, _ = q.shape
+    Skv = k.shape[1]
+    if tuple(lse.shape) != (B, heads, Sq):
+        raise RuntimeError(f"attention_backward: lse must be [{B}, {heads}, {Sq}]")
+    dq = torch.empty((B, Sq, heads * 64), dtype=BF16, device=q.device)
+    dk = torch.empty((B, Skv, heads * 64), dtype=BF16, device=q.device)
+    dv = torch.empty((B, Skv, heads * 64), dtype=BF16, device=q.device)
+    ws = torch.empty(lib.vgpa_attention_bwd_workspace_bytes(B, heads, Sq), dtype=torch.uint8, device=q.device)
+    a = AttentionBwdArgs()
+    a.q, a.k, a.v, a.out, a.d_out, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr()
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.B, a.H, a.Sq, a.Skv, a.head_dim = B, heads, Sq, Skv, 64
+    a.scale = scale
+    a.q_row_stride, a.k_row_stride, a.v_row_stride, a.out_row_stride = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
+    a.dout_row_stride, a.dq_row_stride, a.dk_row_stride, a.dv_row_stride = d_out.stride(1), dq.stride(1), dk.stride(1), dv.stride(1)
+    a.q_batch_stride, a.k_batch_stride, a.v_batch_stride, a.out_batch_stride = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    a.dout_batch_stride, a.dq_batch_stride, a.dk_batch_stride, a.dv_batch_stride = d_out.stride(0), dq.stride(0), dk.stride(0), dv.stride(0)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    _lib.check(lib.vgpa_attention_bwd_bf16(C.byref(a), _lib.current_stream()), "vgpa_attention_bwd_bf16")
+    return dq, dk, dv
 
 
 def layernorm_modulate(x: torch.Tensor, ln_weight: torch.Tensor | None, ln_bias: torch.Tensor | None, *,
