@@ -128,6 +128,7 @@ typedef struct vgpa_attention_bwd_args {
 size_t vgpa_attention_bwd_workspace_bytes(int B, int H, int Sq);
 int vgpa_attention_bwd_bf16(const vgpa_attention_bwd_args* args, void* stream);
 
+
 /* ------------------------------------------------------------------------------------------------
  * K3 — fused LayerNorm + adaLN modulation: out = LN(x) * (1 + scale[b, seg]) + shift[b, seg].
  * Replaces CogVideoXLayerNormZero / AdaLayerNorm / norm_final of CogVideoXTransformer3DModel
@@ -151,6 +152,26 @@ typedef struct vgpa_layernorm_args {
 } vgpa_layernorm_args;
 
 int vgpa_layernorm_modulate_bf16(const vgpa_layernorm_args* args, void* stream);
+
+/* Row-wise backward kernels of CogVideoXBlock for the DPO training step (train/CogVideoX-5B/03_train.py:116-157 back-
+ * propagates into the LoRA factors of to_q / to_k / to_v / to_out.0). */
+/* dx = [add +] d/dx of vgpa_layernorm_modulate_bf16 applied to dy: `fwd` describes the forward call (x, ln_weight, eps,
+ * scale_txt / scale_vid, rows_per_sample, text_rows, mod_stride_b; out / shift / ln_bias are ignored). The modulation
+ * vectors come from the frozen conditioning path and get no gradient. */
+int vgpa_layernorm_modulate_bwd_bf16(const vgpa_layernorm_args* fwd, const void* dy, int64_t ld_dy, const void* add,
+                                     int64_t ld_add, void* dx, int64_t ld_dx, void* stream);
+/* LayerNorm over every 64-column head of x [rows, >=heads*64] with fp32 affine [64] (norm_q / norm_k of
+ * CogVideoXAttnProcessor2_0). backward = 0: out = LN(x) * weight + bias. backward = 1: out = d/dx for the upstream
+ * gradient dy (weight / bias are frozen). */
+int vgpa_head_layernorm_bf16(const void* x, const void* dy, void* out, int64_t rows, int heads, int64_t ldx, int64_t ld_dy,
+                             int64_t ldo, const float* weight, const float* bias, float eps, int backward, void* stream);
+/* GELU(tanh) on n contiguous bf16 values. backward = 0: out = gelu(x). backward = 1: out = dy * gelu'(x). */
+int vgpa_gelu_tanh_bf16(const void* x, const void* dy, void* out, int64_t n, int backward, void* stream);
+/* out[r, :] = [add[r, :] +] x[r, :] * gate[b(r), seg(r)][:]: the adaLN-zero gated residual `hidden + gate * branch` (bf16
+ * product, then bf16 sum) out of place for the training path, and its backward (add = NULL). */
+int vgpa_scale_cols_bf16(const void* x, const void* add, void* out, int rows, int D, int64_t ldx, int64_t ld_add, int64_t ldo,
+                         int rows_per_sample, int text_rows, const void* gate_txt, const void* gate_vid, int64_t gate_stride_b,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conditioning path and patch (un)embedding helpers.

@@ -307,7 +307,7 @@ def test_dpo_shared_step_forward_vs_oracle(lib):
     assert abs(got.loss.item() - want["loss"]) < 5e-2
     assert set(out) == {"val/loss", "val/reward_margin", "val/reward_accuracy", "loss_output"}
     with pytest.raises(RuntimeError):
-        step.training_step(batch)
+        step.training_step(batch)                             # no trainable policy attached (see tests/test_gpu_train.py)
 
 
 def test_full_size_block_vs_oracle(lib):

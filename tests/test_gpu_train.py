@@ -62,3 +62,189 @@ def test_attention_backward_fused_qkv_views(lib):
     dq, dk, dv = dense.attention_backward(qc, kc, vc, out, d_out.cuda(), lse, H)
     for got, ref in ((dq, dq_ref), (dk, dk_ref), (dv, dv_ref)):
         assert relmax(got.cpu(), ref) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- row-wise backward kernels
+def test_layernorm_modulate_backward_vs_autograd(lib):
+    import ctypes as C
+    from videogpa_b200 import _lib
+    from videogpa_b200.train_dit import _ln_args
+    L = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    B, S, St, D = 2, 37, 5, 512
+    x = torch.randn(B * S, D, generator=g).to(BF)
+    w = (1 + 0.2 * torch.randn(D, generator=g)).to(BF)
+    bias = (0.1 * torch.randn(D, generator=g)).to(BF)
+    mod = (0.5 * torch.randn(B, 4 * D, generator=g)).to(BF)          # per sample: scale_txt | scale_vid | (unused shifts)
+    dy = torch.randn(B * S, D, generator=g).to(BF)
+    add = torch.randn(B * S, D, generator=g).to(BF)
+    xf = x.float().requires_grad_(True)
+    scale = torch.empty(B * S, D)
+    for b in range(B):
+        scale[b * S:b * S + St] = mod[b, :D].float()
+        scale[b * S + St:(b + 1) * S] = mod[b, D:2 * D].float()
+    y = torch.nn.functional.layer_norm(xf, (D,), w.float(), bias.float(), 1e-5) * (1 + scale)
+    y.backward(dy.float())
+    ref = xf.grad + add.float()
+    xc, dyc, addc, modc, wc = x.cuda(), dy.cuda(), add.cuda(), mod.cuda(), w.cuda()
+    dx = torch.empty_like(xc)
+    a = _ln_args(xc, wc, 1e-5, (S, St), modc[:, :D], modc[:, D:2 * D], 4 * D)
+    _lib.check(L.vgpa_layernorm_modulate_bwd_bf16(C.byref(a), dyc.data_ptr(), D, addc.data_ptr(), D, dx.data_ptr(), D, _lib.current_stream()), "ln bwd")
+    assert relmax(dx.cpu(), ref) < 1e-2
+    # plain LayerNorm without affine / modulation / add
+    xf2 = x.float().requires_grad_(True)
+    torch.nn.functional.layer_norm(xf2, (D,), None, None, 1e-5).backward(dy.float())
+    a2 = _ln_args(xc, None, 1e-5, (0, 0), None, None, 0)
+    _lib.check(L.vgpa_layernorm_modulate_bwd_bf16(C.byref(a2), dyc.data_ptr(), D, None, 0, dx.data_ptr(), D, _lib.current_stream()), "ln bwd")
+    assert relmax(dx.cpu(), xf2.grad) < 1e-2
+
+
+def test_head_layernorm_gelu_gate_kernels_vs_autograd(lib):
+    from videogpa_b200 import _lib
+    from videogpa_b200.train_dit import _Gelu, _GateRes, _HeadLN
+    g = torch.Generator().manual_seed(2)
+    M, heads = 50, 3
+    D = heads * 64
+    qkv = torch.randn(M, 3 * D, generator=g).to(BF)
+    lnq = ((1 + 0.2 * torch.randn(64, generator=g)), 0.1 * torch.randn(64, generator=g))
+    lnk = ((1 + 0.2 * torch.randn(64, generator=g)), 0.1 * torch.randn(64, generator=g))
+    dy = torch.randn(M, 3 * D, generator=g).to(BF)
+    xf = qkv.float().requires_grad_(True)
+    parts = []
+    for i, (w, b) in enumerate((lnq, lnk)):
+        parts.append(torch.nn.functional.layer_norm(xf[:, i * D:(i + 1) * D].reshape(M, heads, 64), (64,), w, b, 1e-6).reshape(M, D))
+    ref = torch.cat(parts + [xf[:, 2 * D:]], dim=1)
+    ref.backward(dy.float())
+    xc = qkv.cuda().requires_grad_(True)
+    out = _HeadLN.apply(xc, heads, tuple(t.cuda() for t in lnq), tuple(t.cuda() for t in lnk), 1e-6)
+    out.backward(dy.cuda())
+    assert relmax(out.detach().cpu(), ref.detach()) < 1e-2 and relmax(xc.grad.cpu(), xf.grad) < 1e-2
+    # GELU(tanh)
+    x = (2 * torch.randn(40, 64, generator=g)).to(BF)
+    d = torch.randn(40, 64, generator=g).to(BF)
+    xf = x.float().requires_grad_(True)
+    r = torch.nn.functional.gelu(xf, approximate="tanh")
+    r.backward(d.float())
+    xc = x.cuda().requires_grad_(True)
+    o = _Gelu.apply(xc)
+    o.backward(d.cuda())
+    assert relmax(o.detach().cpu(), r.detach()) < 1e-2 and relmax(xc.grad.cpu(), xf.grad) < 1e-2
+    # gated residual: hidden + gate[b, seg] * branch
+    B, S, St, D = 2, 11, 3, 64
+    hid, br = torch.randn(B * S, D, generator=g).to(BF), torch.randn(B * S, D, generator=g).to(BF)
+    gates = torch.randn(B, 2 * D, generator=g).to(BF)
+    gfull = torch.empty(B * S, D)
+    for b in range(B):
+        gfull[b * S:b * S + St] = gates[b, :D].float()
+        gfull[b * S + St:(b + 1) * S] = gates[b, D:].float()
+    d = torch.randn(B * S, D, generator=g).to(BF)
+    hc, bc, gc = hid.cuda().requires_grad_(True), br.cuda().requires_grad_(True), gates.cuda()
+    o = _GateRes.apply(hc, bc, (S, St), gc[:, :D], gc[:, D:], 2 * D)
+    o.backward(d.cuda())
+    want = (hid.float() + (gfull * br.float()).to(BF).float()).to(BF)
+    assert torch.equal(o.detach().cpu(), want)                                     # bf16 product, then bf16 sum: bit-exact
+    assert torch.equal(hc.grad.cpu(), d) and torch.equal(bc.grad.cpu(), (d.float() * gfull).to(BF))
+
+
+# ---------------------------------------------------------------------------------------------- the whole training step
+def _torch_dpo_loss(vw, vl, rw, rl, tw, tl, beta):
+    err = lambda a, b: ((a - b) ** 2).reshape(a.shape[0], -1).mean(dim=1)
+    logits = beta * ((err(rw, tw) - err(vw, tw)) - (err(rl, tl) - err(vl, tl)))
+    return torch.nn.functional.softplus(-logits).mean()
+
+
+def test_dpo_training_step_gradients_vs_oracle_autograd(lib):
+    """training_step + backward() against torch autograd through the oracle DiT (fp32, CPU) with the LoRA delta merged into the
+    policy weights (the same function of A, B as PEFT's unmerged branch): loss and every dA / dB within 6e-2 of the tensor max
+    (two blocks of bf16 forward + backward; most tensors agree to ~1e-2)."""
+    from oracle import dit_torch as O
+    from videogpa_b200.train_dit import TARGETS, LoRATrainableTransformer
+    from videogpa_b200.train_step import DPOSharedStep
+    from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+    kw = dict(num_attention_heads=4, num_layers=2, text_embed_dim=256, sample_width=24, sample_height=16, sample_frames=9, max_text_seq_length=18)
+    ocfg = O.DiTConfig(**kw)
+    sd = {k: v.to(BF).float() for k, v in O.random_state_dict(ocfg, seed=7, randomize_norms=True, std=0.05).items()}
+    base = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
+    pol = LoRATrainableTransformer(base, r=64, lora_alpha=128.0, seed=3)
+    g = torch.Generator().manual_seed(31)
+    D = 256
+    ref_params = {}
+    for layer in range(2):
+        for m in TARGETS:
+            A = (0.05 * torch.randn(64, D, generator=g)).to(BF).float()
+            Bm = (0.05 * torch.randn(D, 64, generator=g)).to(BF).float()
+            with torch.no_grad():
+                pol.lora[layer][m][0].copy_(A)
+                pol.lora[layer][m][1].copy_(Bm)
+            ref_params[(layer, m)] = (A.clone().requires_grad_(True), Bm.clone().requires_grad_(True))
+    Bsz, C, Fr, H, W, St = 2, 16, 3, 16, 24, 18
+    batch = {"x_win": torch.randn(Bsz, C, Fr, H, W, generator=g), "x_lose": torch.randn(Bsz, C, Fr, H, W, generator=g),
+             "prompt_emb": torch.randn(Bsz, St, 256, generator=g).to(BF)}
+    t = torch.tensor([812, 77])
+    noise = torch.randn(Bsz, Fr, C, H, W, generator=g)
+    beta = 50.0                                                    # a logit of O(1) so that the sigmoid factor matters
+    step = DPOSharedStep(base, None, beta=beta, trainable=pol)
+    loss = step.training_step(batch, timesteps=t.cuda(), noise=noise.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+
+    # oracle: merged policy weights as differentiable functions of A, B
+    sd_pol = dict(sd)
+    for (layer, m), (A, Bm) in ref_params.items():
+        k = f"transformer_blocks.{layer}.attn1.{m}.weight"
+        sd_pol[k] = sd[k] + 2.0 * (Bm @ A)
+    ac = O.cogvideox_alphas_cumprod()
+    xw, xl = batch["x_win"].permute(0, 2, 1, 3, 4), batch["x_lose"].permute(0, 2, 1, 3, 4)
+    fw = lambda s_, x: O.transformer_forward(s_, ocfg, O.add_noise(ac, x, noise, t.numpy()), batch["prompt_emb"].float(), t, None)
+    with torch.no_grad():
+        rw, rl = fw(sd, xw), fw(sd, xl)
+    want = _torch_dpo_loss(fw(sd_pol, xw), fw(sd_pol, xl), rw, rl, O.get_velocity(ac, xw, noise, t.numpy()),
+                           O.get_velocity(ac, xl, noise, t.numpy()), beta)
+    want.backward()
+    assert abs(loss.item() - want.item()) < 5e-2, (loss.item(), want.item())
+    worst = 0.0
+    for (layer, m), (A, Bm) in ref_params.items():
+        gA, gB = pol.lora[layer][m][0].grad, pol.lora[layer][m][1].grad
+        assert gA is not None and gB is not None and gA.dtype == torch.float32
+        ea, eb = relmax(gA.cpu(), A.grad), relmax(gB.cpu(), Bm.grad)
+        worst = max(worst, ea, eb)
+        assert ea < 6e-2 and eb < 6e-2, (layer, m, ea, eb)
+    # gradient checkpointing must not change the result
+    pol2 = LoRATrainableTransformer(base, r=64, lora_alpha=128.0, seed=3, gradient_checkpointing=False)
+    for layer in range(2):
+        for m in TARGETS:
+            with torch.no_grad():
+                pol2.lora[layer][m][0].copy_(pol.lora[layer][m][0])
+                pol2.lora[layer][m][1].copy_(pol.lora[layer][m][1])
+    step2 = DPOSharedStep(base, None, beta=beta, trainable=pol2)
+    step2.training_step(batch, timesteps=t.cuda(), noise=noise.cuda()).backward()
+    for layer in range(2):
+        for m in TARGETS:
+            assert torch.equal(pol2.lora[layer][m][0].grad, pol.lora[layer][m][0].grad)
+    # one optimizer step (AdamW, lr 5e-6 as in 03_train.py:207-210) moves every factor
+    opt = step.configure_optimizers()
+    before = pol.lora[1]["to_q"][0].detach().clone()
+    opt.step()
+    assert not torch.equal(before, pol.lora[1]["to_q"][0].detach())
+    names = [n for n, _ in pol.named_parameters()]
+    assert names[0] == "base_model.model.transformer_blocks.0.attn1.to_q.lora_A.weight" and len(names) == 16
+
+
+def test_training_forward_matches_inference_with_zero_lora(lib):
+    """With B = 0 (PEFT's initial state) the differentiable forward equals the inference transformer called without rotary
+    embeddings up to the different rounding points of the unfused training path (<= 2e-2 of the max)."""
+    from oracle import dit_torch as O
+    from videogpa_b200.train_dit import LoRATrainableTransformer
+    from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+    kw = dict(num_attention_heads=4, num_layers=2, text_embed_dim=256, sample_width=24, sample_height=16, sample_frames=9, max_text_seq_length=18)
+    sd = {k: v.to(BF).float() for k, v in O.random_state_dict(O.DiTConfig(**kw), seed=8, randomize_norms=True, std=0.05).items()}
+    base = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
+    pol = LoRATrainableTransformer(base)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(4, 3, 16, 16, 24, generator=g).cuda()
+    e = torch.randn(4, 18, 256, generator=g).to(BF).cuda()
+    t = torch.tensor([5, 300, 700, 999]).cuda()
+    with torch.no_grad():
+        a = pol(x, e, t)
+        b = base(x, encoder_hidden_states=e, timestep=t).sample
+    assert a.shape == b.shape and relmax(a, b) < 2e-2

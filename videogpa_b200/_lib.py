@@ -137,6 +137,10 @@ SIGNATURES = {
     "vgpa_attention_bf16": (c_int, [C.POINTER(AttentionArgs), c_void_p]),
     "vgpa_attention_bwd_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
     "vgpa_attention_bwd_bf16": (c_int, [C.POINTER(AttentionBwdArgs), c_void_p]),
+    "vgpa_layernorm_modulate_bwd_bf16": (c_int, [C.POINTER(LayerNormArgs), c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
+    "vgpa_head_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_float, c_int, c_void_p]),
+    "vgpa_gelu_tanh_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "vgpa_scale_cols_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_int, c_int, c_void_p, c_void_p, c_i64, c_void_p]),
     "vgpa_layernorm_modulate_bf16": (c_int, [C.POINTER(LayerNormArgs), c_void_p]),
     "vgpa_linear_smallm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_i64, c_int, c_void_p]),
     "vgpa_timestep_embedding_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -115,7 +115,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
 
 
 def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor,
-                       lse: torch.Tensor, heads: int, *, scale: float = 0.0):
+                       lse: torch.Tensor, heads: int, *, scale: float = 0.0, grads=None):
     """(dq, dk, dv) of `attention` (head_dim 64) from the saved output and logsumexp; see vgpa_attention_bwd_bf16."""
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (d_out, "d_out")):
@@ -127,9 +127,16 @@ def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: t
     Skv = k.shape[1]
     if tuple(lse.shape) != (B, heads, Sq):
         raise RuntimeError(f"attention_backward: lse must be [{B}, {heads}, {Sq}]")
-    dq = torch.empty((B, Sq, heads * 64), dtype=BF16, device=q.device)
-    dk = torch.empty((B, Skv, heads * 64), dtype=BF16, device=q.device)
-    dv = torch.empty((B, Skv, heads * 64), dtype=BF16, device=q.device)
+    if grads is not None:                                 # caller-provided (dq, dk, dv), e.g. column slices of one buffer
+        dq, dk, dv = grads
+        for t, n in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
+            _req(t, BF16, n, contiguous=False)
+            if t.dim() != 3 or t.stride(2) != 1:
+                raise RuntimeError(f"attention_backward: {n} must be [B, S, cols] with a contiguous last dimension")
+    else:
+        dq = torch.empty((B, Sq, heads * 64), dtype=BF16, device=q.device)
+        dk = torch.empty((B, Skv, heads * 64), dtype=BF16, device=q.device)
+        dv = torch.empty((B, Skv, heads * 64), dtype=BF16, device=q.device)
     ws = torch.empty(lib.vgpa_attention_bwd_workspace_bytes(B, heads, Sq), dtype=torch.uint8, device=q.device)
     a = AttentionBwdArgs()
     a.q, a.k, a.v, a.out, a.d_out, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr()

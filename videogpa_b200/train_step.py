@@ -9,8 +9,9 @@ reference's `validation_step` (:189-201) runs under `torch.no_grad()`:
     loss_fn(v_win_pred, v_lose_pred, v_win_ref, v_lose_ref, v_win_target, v_lose_target) -> LossOutput
 
 The winner and the loser share noise, timestep and prompt, so each model sees them as one batch of 2B samples (one pass over
-its weights). The four forwards run on the sm_100a DiT kernels and the loss on the fused DPO kernel. The backward pass
-(attention / GEMM dgrad, LoRA wgrad) is not built: `training_step` raises, `validation_step` is complete.
+its weights). The four forwards run on the sm_100a DiT kernels and the loss on the fused DPO kernel. `training_step` runs the
+policy through videogpa_b200.train_dit (differentiable forward, hand-written backward kernels, LoRA factors as the only
+trainable parameters) and returns the loss for `backward()`.
 """
 from __future__ import annotations
 
@@ -21,14 +22,16 @@ from .schedulers import CogVideoXDPMScheduler
 
 
 class DPOSharedStep:
-    def __init__(self, transformer, ref_transformer, beta: float = 1.0, scheduler=None):
+    def __init__(self, transformer, ref_transformer, beta: float = 1.0, scheduler=None, trainable=None):
+        """transformer / ref_transformer: policy and reference for the forward-only path (validation_step). trainable: a
+        train_dit.LoRATrainableTransformer — the policy of training_step; its frozen base doubles as the reference model."""
         self.transformer, self.ref_transformer = transformer, ref_transformer
+        self.trainable = trainable
         self.scheduler = scheduler or CogVideoXDPMScheduler()
         self.loss_fn = create_loss_strategy(strategy="dpo", beta=beta)
         self.device = transformer.device
 
-    @torch.no_grad()
-    def _shared_step(self, batch: dict, generator=None, timesteps=None, noise=None) -> LossOutput:
+    def _prepare(self, batch: dict, generator=None, timesteps=None, noise=None):
         dev = self.device
         x_win = batch["x_win"].to(dev).permute(0, 2, 1, 3, 4).float()            # [B, F, C, H, W]
         x_lose = batch["x_lose"].to(dev).permute(0, 2, 1, 3, 4).float()
@@ -43,12 +46,17 @@ class DPOSharedStep:
         pair = torch.cat([x_win_noisy, x_lose_noisy], dim=0)                     # one batch of 2B per model
         emb2 = torch.cat([prompt_emb, prompt_emb], dim=0)
         t2 = torch.cat([timesteps, timesteps], dim=0)
-        v_pred = self.transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
-        v_ref = self.ref_transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
         v_win_target = self.scheduler.get_velocity(x_win, noise, timesteps)
         v_lose_target = self.scheduler.get_velocity(x_lose, noise, timesteps)
+        return B, pair, emb2, t2, v_win_target.contiguous(), v_lose_target.contiguous()
+
+    @torch.no_grad()
+    def _shared_step(self, batch: dict, generator=None, timesteps=None, noise=None) -> LossOutput:
+        B, pair, emb2, t2, v_win_target, v_lose_target = self._prepare(batch, generator, timesteps, noise)
+        v_pred = self.transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
+        v_ref = self.ref_transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
         return self.loss_fn(v_pred[:B].contiguous(), v_pred[B:].contiguous(), v_ref[:B].contiguous(), v_ref[B:].contiguous(),
-                            v_win_target.contiguous(), v_lose_target.contiguous())
+                            v_win_target, v_lose_target)
 
     def validation_step(self, batch: dict, batch_idx: int = 0, **kw) -> dict:
         """-> the scalars the reference logs (:189-201): val/loss, val/reward_margin, val/reward_accuracy."""
@@ -56,6 +64,30 @@ class DPOSharedStep:
         return {"val/loss": out.loss, "val/reward_margin": out.reward_margin,
                 "val/reward_accuracy": (out.reward_margin > 0).float().mean(), "loss_output": out}
 
-    def training_step(self, batch: dict, batch_idx: int = 0):
-        raise RuntimeError("the DPO training step needs the DiT backward kernels (attention / GEMM dgrad, LoRA wgrad), which are "
-                           "not built in this round (SURVEY.md §8 f-2); validation_step / _shared_step (forward) are available")
+    def training_step(self, batch: dict, batch_idx: int = 0, generator=None, timesteps=None, noise=None) -> torch.Tensor:
+        """`training_step` of the reference (:159-187): returns the differentiable DPO loss; `loss.backward()` runs the hand-
+        written backward kernels down to the LoRA factors (train_dit). The reference forwards run without a graph on the
+        frozen base shared with the policy."""
+        if self.trainable is None:
+            raise RuntimeError("training_step needs `trainable=LoRATrainableTransformer(transformer)` (videogpa_b200.train_dit)")
+        B, pair, emb2, t2, v_win_target, v_lose_target = self._prepare(batch, generator, timesteps, noise)
+        with torch.no_grad():
+            ref = self.ref_transformer if self.ref_transformer is not None else self.trainable.base
+            v_ref = ref(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
+        v_pred = self.trainable(pair, emb2, t2)
+        out = self.loss_fn(v_pred[:B].contiguous(), v_pred[B:].contiguous(), v_ref[:B].contiguous(), v_ref[B:].contiguous(),
+                           v_win_target, v_lose_target)
+        self.last_output = out
+        return out.loss
+
+    def fit_step(self, batch: dict, optimizer, **kw) -> float:
+        """zero_grad -> training_step -> backward -> optimizer.step (what the Lightning trainer does around training_step)."""
+        optimizer.zero_grad(set_to_none=True)
+        loss = self.training_step(batch, **kw)
+        loss.backward()
+        optimizer.step()
+        return float(loss.detach())
+
+    def configure_optimizers(self, lr: float = 5e-6):
+        """`torch.optim.AdamW(self.transformer.parameters(), lr=5e-6)` over the trainable (LoRA) parameters (:207-210)."""
+        return torch.optim.AdamW(self.trainable.parameters(), lr=lr)
