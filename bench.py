@@ -387,6 +387,38 @@ def run_ours(args, rank, world, local):
     except Exception as ex:
         wan = {"error": str(ex)}
 
+    # ---- DPO training step (BASELINE.json configs[4] per-GPU work: one preference pair, LoRA r = 64 on to_q/k/v/out of all 42 blocks,
+    #      gradient checkpointing; 2 reference + 2 policy forwards, recompute, backward, AdamW), reported beside
+    train = None
+    if world == 1:
+        try:
+            from videogpa_b200.train_dit import LoRATrainableTransformer
+            from videogpa_b200.train_step import DPOSharedStep
+            pol = LoRATrainableTransformer(model, r=64, lora_alpha=128.0)
+            dstep = DPOSharedStep(model, None, beta=1.0, trainable=pol)
+            opt = dstep.configure_optimizers()
+            gt = torch.Generator().manual_seed(0)
+            tb = {"x_win": torch.randn(1, 16, 13, 60, 90, generator=gt), "x_lose": torch.randn(1, 16, 13, 60, 90, generator=gt),
+                  "prompt_emb": torch.randn(1, S_TEXT, 4096, generator=gt).to(torch.bfloat16)}
+            dstep.fit_step(tb, opt)                               # warm-up: builds the transposed dgrad weights
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            opt.zero_grad(set_to_none=True)
+            tl = dstep.training_step(tb)
+            ev[1].record()
+            tl.backward()
+            opt.step()
+            ev[2].record(); torch.cuda.synchronize()
+            tms = ev[0].elapsed_time(ev[2])
+            train = {"metric": "DPO training step, CogVideoX-5B 49f 720x480, 1 preference pair per GPU", "ms_per_step": tms,
+                     "pairs_per_s": 1000.0 / tms, "forward_ms": ev[0].elapsed_time(ev[1]), "backward_ms": ev[1].elapsed_time(ev[2]),
+                     "loss": float(tl.detach()), "lora_params": sum(p.numel() for p in pol.parameters()),
+                     "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30, "weights": "random-init base, PEFT-initialised LoRA"}
+            del pol, dstep, opt, tl
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            train = {"error": str(ex)}
+
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -407,7 +439,7 @@ def run_ours(args, rank, world, local):
                      "flops_per_launch": attn_flops, "avg_launch_ms": attn_avg_ms, "launches_timed": len(attn_ms),
                      "share_of_step": (sum(attn_ms) / ms_max) if ms_max > 0 else None},
         "step_tflops": step_flops * args.steps / (ms_max / 1000.0) / 1e12, "kernel_families": families,
-        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae, "encoders": enc_leg, "wan_step": wan,
+        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae, "encoders": enc_leg, "wan_step": wan, "dpo_train_step": train,
     }
     print(json.dumps(line), flush=True)
 

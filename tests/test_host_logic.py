@@ -121,7 +121,7 @@ def test_product_path_fails_loudly_without_cuda():
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["VGPA_ROOT"])
-from videogpa_b200.parallel import CfgPairGroup, gather_frames, gather_scores, init_from_env, shard_round_robin
+from videogpa_b200.parallel import CfgPairGroup, average_gradients, gather_frames, gather_scores, init_from_env, shard_round_robin
 rank, world, _ = init_from_env("gloo")
 assert world == 2
 grp = CfgPairGroup(rank, world)
@@ -143,6 +143,14 @@ else:
 s = gather_scores(torch.arange(rank + 2, dtype=torch.float64) + 10 * rank, rank, world)
 assert s.tolist() == [0.0, 1.0, 10.0, 11.0, 12.0]
 assert shard_round_robin(range(5), rank, world) == ([0, 2, 4] if rank == 0 else [1, 3])
+# DDP exchange of the training step: gradients averaged in place, a missing gradient counts as zero, buckets split by size
+ps = [torch.zeros(3, 4, requires_grad=True), torch.zeros(5, requires_grad=True), torch.zeros(2, 2, requires_grad=True)]
+ps[0].grad = torch.full((3, 4), float(rank + 1))
+ps[1].grad = torch.arange(5.0) * (rank + 1)
+if rank == 0:
+    ps[2].grad = torch.ones(2, 2)
+assert average_gradients(ps, bucket_bytes=64) == 2          # 12 + 5 floats exceed 64 bytes -> [p0], [p1, p2]
+assert torch.all(ps[0].grad == 1.5) and torch.equal(ps[1].grad, torch.arange(5.0) * 1.5) and torch.all(ps[2].grad == 0.5)
 dist.barrier(); dist.destroy_process_group()
 print("worker ok", rank)
 '''

@@ -137,3 +137,45 @@ def gather_scores(scores: torch.Tensor, rank: int, world: int):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad)
     return torch.cat([b[:int(c.item())] for b, c in zip(bufs, counts)])
+
+
+def average_gradients(params, group=None, bucket_bytes: int = 256 << 20) -> int:
+    """The data-path collective of the DPO training step (config 5: DDP over the GPUs of one box; Lightning's
+    `strategy="ddp"` in train/CogVideoX-5B/03_train.py:258-266): all-reduce-average the `.grad` of `params` in place.
+
+    Only the LoRA factors train (66 M fp32 values = 264 MB for CogVideoX-5B at r = 64), so the gradients are packed into
+    flat fp32 buckets of at most `bucket_bytes` and reduced with one NCCL all-reduce per bucket (NVSwitch reduces in the
+    switch when NVLS is available; the bucket is sized for launch latency, not link count). Parameters without a gradient
+    contribute zeros so that every rank issues the same collectives. Returns the number of collectives issued."""
+    import torch.distributed as dist
+    params = [p for p in params]
+    world = dist.get_world_size(group)
+    if world == 1 or not params:
+        return 0
+    calls = 0
+    i = 0
+    while i < len(params):
+        n, j = 0, i
+        while j < len(params) and (j == i or (n + params[j].numel()) * 4 <= bucket_bytes):
+            n += params[j].numel()
+            j += 1
+        ref = params[i]
+        flat = torch.zeros(n, dtype=torch.float32, device=ref.device)
+        off = 0
+        for p in params[i:j]:
+            if p.grad is not None:
+                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+            off += p.numel()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        calls += 1
+        off = 0
+        for p in params[i:j]:
+            g = flat[off:off + p.numel()].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += p.numel()
+        i = j
+    return calls

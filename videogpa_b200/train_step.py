@@ -80,11 +80,17 @@ class DPOSharedStep:
         self.last_output = out
         return out.loss
 
-    def fit_step(self, batch: dict, optimizer, **kw) -> float:
-        """zero_grad -> training_step -> backward -> optimizer.step (what the Lightning trainer does around training_step)."""
+    def fit_step(self, batch: dict, optimizer, process_group=None, **kw) -> float:
+        """zero_grad -> training_step -> backward -> (DDP gradient average) -> optimizer.step: what the Lightning trainer
+        (`strategy="ddp"`, 03_train.py:258-266) does around training_step. With torch.distributed initialised every rank
+        runs its own pairs and the LoRA gradients are all-reduced (parallel.average_gradients)."""
+        import torch.distributed as dist
         optimizer.zero_grad(set_to_none=True)
         loss = self.training_step(batch, **kw)
         loss.backward()
+        if dist.is_available() and dist.is_initialized():
+            from .parallel import average_gradients
+            average_gradients(self.trainable.parameters(), group=process_group)
         optimizer.step()
         return float(loss.detach())
 
