@@ -12,16 +12,19 @@
 //       S^T = K Q^T, dP^T = V dO^T -> TMEM; threads own key rows, L / delta of the 128 queries come from shared memory;
 //       dV += P^T dO_i and dK += dS^T Q_i are TS MMAs with the dO / Q tiles read MN-major.
 // TMEM: dq kernel 384 columns (S 128, dP 128, dS 64, dQ 64); dkv kernel 512 (S^T, dP^T 128 each; P^T, dS^T, dV, dK 64 each).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (elect.sync), warps 2-5 compute. First version: the MMA and the
-// compute phase of one tile alternate (single-buffered S / dP), so the tensor pipe idles while dS is computed.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (elect.sync), warps 2-9 compute: two warps per TMEM lane quarter,
+// each owning 64 of the 128 columns of its rows; the dS arithmetic runs as packed f32x2 FMA-pipe ops and the softmax scale
+// is applied once in the dQ / dK epilogue. The MMA and the compute phase of one tile still alternate (single-buffered
+// S / dP), so the tensor pipe idles while dS is computed.
 #include "sm100.cuh"
+#include "attn_common.cuh"
 #include "../../include/videogpa_b200.h"
 #include <math.h>
 
 namespace vgpa {
 namespace {
 
-constexpr int AB_THREADS = 192;
+constexpr int AB_THREADS = 320;                             // TMA warp, MMA warp, 2 x 4 compute warps
 constexpr int AB_T = 128;                                   // tile rows (queries or keys)
 constexpr int AB_D = 64;
 constexpr uint32_t AB_TILE = AB_T * AB_D * 2;               // 16384 bytes
@@ -39,26 +42,30 @@ struct BwdParams {
   float scale, scale_log2;
 };
 
-__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, uint32_t tmem_addr) {
-#pragma unroll
-  for (int c = 0; c < AB_D / 16; ++c) {
+// columns [16*c_begin, 16*c_end) of a 64-column fp32 accumulator row -> bf16 global, times `mul`
+__device__ __forceinline__ void store_cols(__nv_bfloat16* dst, uint32_t tmem_addr, int c_begin, int c_end, float mul) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t o[16];
     ptx::tmem_ld_32x16(tmem_addr + c * 16, o);
     ptx::tmem_ld_wait();
     if (dst != nullptr) {
-      uint4 v0, v1;
-      v0.x = pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1]));
-      v0.y = pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3]));
-      v0.z = pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5]));
-      v0.w = pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7]));
-      v1.x = pack_bf16x2(__uint_as_float(o[8]), __uint_as_float(o[9]));
-      v1.y = pack_bf16x2(__uint_as_float(o[10]), __uint_as_float(o[11]));
-      v1.z = pack_bf16x2(__uint_as_float(o[12]), __uint_as_float(o[13]));
-      v1.w = pack_bf16x2(__uint_as_float(o[14]), __uint_as_float(o[15]));
-      reinterpret_cast<uint4*>(dst + c * 16)[0] = v0;
-      reinterpret_cast<uint4*>(dst + c * 16)[1] = v1;
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(o[2 * i]) * mul, __uint_as_float(o[2 * i + 1]) * mul);
+      reinterpret_cast<uint4*>(dst + c * 16)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      reinterpret_cast<uint4*>(dst + c * 16)[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
   }
+}
+
+using attn::f2_pack;
+using attn::f2_unpack;
+using attn::f2_fma;
+using attn::f2_add;
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // ------------------------------------------------------------------------------------------------ dQ
@@ -91,7 +98,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     ptx::mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
     ptx::mbar_init(sdp_full, 1);
-    ptx::mbar_init(ds_ready, 128);
+    ptx::mbar_init(ds_ready, 256);
     ptx::mbar_init(dq_done, 1);
     ptx::fence_barrier_init();
   }
@@ -154,6 +161,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
   } else {
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                         // which 64 of the 128 kv columns this warp handles
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int row = m0 + r;
@@ -161,30 +169,34 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const long long stat = (static_cast<long long>(batch) * prm.H + head) * prm.Sq + (live ? row : 0);
     const float L = live ? prm.lse[stat] : INFINITY;          // rows past the end get P = 0
     const float dl = live ? prm.delta[stat] : 0.f;
-    const float sc = prm.scale_log2, scale = prm.scale;
+    const uint64_t sc2 = f2_pack(prm.scale_log2, prm.scale_log2), negL2 = f2_pack(-L, -L), negdl2 = f2_pack(-dl, -dl);
     const int tail = prm.Skv - (nkv - 1) * AB_T;
     for (int j = 0; j < nkv; ++j) {
       ptx::mbar_wait(sdp_full, j & 1);
       ptx::tc_fence_after();
       const int valid = (j == nkv - 1) ? tail : AB_T;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t s[32], dp[32], pk[16];
         ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_S + c * 32, s);
         ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_DP + c * 32, dp);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float d0, d1;
-          {
-            const float p = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * i]), sc, -L));
-            d0 = (c * 32 + 2 * i < valid) ? p * (__uint_as_float(dp[2 * i]) - dl) * scale : 0.f;
-          }
-          {
-            const float p = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sc, -L));
-            d1 = (c * 32 + 2 * i + 1 < valid) ? p * (__uint_as_float(dp[2 * i + 1]) - dl) * scale : 0.f;
-          }
+          float x0, x1, d0, d1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, negL2), x0, x1);
+          const uint64_t p2 = f2_pack(ptx::ex2_approx(x0), ptx::ex2_approx(x1));
+          f2_unpack(f2_mul(p2, f2_add(f2_pack(__uint_as_float(dp[2 * i]), __uint_as_float(dp[2 * i + 1])), negdl2)), d0, d1);
           pk[i] = pack_bf16x2(d0, d1);
+        }
+        if (valid < AB_T) {                                   // last kv tile: columns past the end contribute nothing
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = c * 32 + 2 * i;
+            if (col >= valid) pk[i] = 0u;
+            else if (col + 1 >= valid) pk[i] &= 0x0000ffffu;
+          }
         }
         ptx::tmem_st_32x16(tmem_base + lane_addr + DQ_COL_DS + c * 16, pk);
       }
@@ -197,7 +209,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __nv_bfloat16* dst = live ? prm.dq + static_cast<long long>(batch) * prm.dq_batch_stride +
                                     static_cast<long long>(row) * prm.dq_row_stride + head * AB_D
                               : nullptr;
-    store_row64(dst, tmem_base + lane_addr + DQ_COL_DQ);
+    store_cols(dst, tmem_base + lane_addr + DQ_COL_DQ, half * 2, half * 2 + 2, prm.scale);   // dS was formed without the scale
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -237,7 +249,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     ptx::mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 1); }
     ptx::mbar_init(sdp_full, 1);
-    ptx::mbar_init(ds_ready, 128);
+    ptx::mbar_init(ds_ready, 256);
     ptx::mbar_init(acc_done, 1);
     ptx::fence_barrier_init();
   }
@@ -305,25 +317,27 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;                    // key row inside the tile
+    const int half = (warp - 2) >> 2;                         // which 64 of the 128 query columns this warp handles
+    const int r = quarter * 32 + lane;                        // key row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const long long stat0 = (static_cast<long long>(batch) * prm.H + head) * prm.Sq;
-    const float sc = prm.scale_log2, scale = prm.scale;
+    const uint64_t sc2 = f2_pack(prm.scale_log2, prm.scale_log2);
     for (int i = 0; i < nq; ++i) {
       const int slot = i & 1;
-      {
+      if (half == 0) {                                        // -L and -delta of the tile's 128 queries
         const int q = i * AB_T + r;
         const bool ok = q < prm.Sq;
-        sL[slot * AB_T + r] = ok ? prm.lse[stat0 + q] : INFINITY;      // queries past the end: P = 0
-        sDl[slot * AB_T + r] = ok ? prm.delta[stat0 + q] : 0.f;
+        sL[slot * AB_T + r] = ok ? -prm.lse[stat0 + q] : -INFINITY;    // queries past the end: P = 0
+        sDl[slot * AB_T + r] = ok ? -prm.delta[stat0 + q] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       ptx::mbar_wait(sdp_full, i & 1);
       ptx::tc_fence_after();
       const float* Lq = sL + slot * AB_T;
       const float* Dq = sDl + slot * AB_T;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t s[32], dp[32], pp[16], pd[16];
         ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_ST + c * 32, s);
         ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_DPT + c * 32, dp);
@@ -331,10 +345,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const int q0 = c * 32 + 2 * k;
-          const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * k]), sc, -Lq[q0]));
-          const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * k + 1]), sc, -Lq[q0 + 1]));
-          const float d0 = p0 * (__uint_as_float(dp[2 * k]) - Dq[q0]) * scale;
-          const float d1 = p1 * (__uint_as_float(dp[2 * k + 1]) - Dq[q0 + 1]) * scale;
+          const uint64_t negL2 = *reinterpret_cast<const uint64_t*>(Lq + q0);
+          const uint64_t negdl2 = *reinterpret_cast<const uint64_t*>(Dq + q0);
+          float x0, x1, d0, d1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1])), sc2, negL2), x0, x1);
+          const float p0 = ptx::ex2_approx(x0), p1 = ptx::ex2_approx(x1);
+          f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack(__uint_as_float(dp[2 * k]), __uint_as_float(dp[2 * k + 1])), negdl2)), d0, d1);
           pp[k] = pack_bf16x2(p0, p1);
           pd[k] = pack_bf16x2(d0, d1);
         }
@@ -353,8 +369,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                     static_cast<long long>(row) * prm.dv_row_stride + head * AB_D : nullptr;
     __nv_bfloat16* dkp = live ? prm.dk + static_cast<long long>(batch) * prm.dk_batch_stride +
                                     static_cast<long long>(row) * prm.dk_row_stride + head * AB_D : nullptr;
-    store_row64(dvp, tmem_base + lane_addr + KV_COL_DV);
-    store_row64(dkp, tmem_base + lane_addr + KV_COL_DK);
+    store_cols(dvp, tmem_base + lane_addr + KV_COL_DV, half * 2, half * 2 + 2, 1.0f);
+    store_cols(dkp, tmem_base + lane_addr + KV_COL_DK, half * 2, half * 2 + 2, prm.scale);      // dS^T was formed without the scale
   }
   ptx::tc_fence_before();
   __syncthreads();
