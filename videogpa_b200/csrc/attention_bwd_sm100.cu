@@ -11,11 +11,11 @@
 //   * attn_bwd_dkv_kernel: one CTA per (128-key tile, head, sample), loops over query tiles, transposed problem:
 //       S^T = K Q^T, dP^T = V dO^T -> TMEM; threads own key rows, L / delta of the 128 queries come from shared memory;
 //       dV += P^T dO_i and dK += dS^T Q_i are TS MMAs with the dO / Q tiles read MN-major.
-// TMEM: dq kernel 384 columns (S 128, dP 128, dS 64, dQ 64); dkv kernel 512 (S^T, dP^T 128 each; P^T, dS^T, dV, dK 64 each).
+// TMEM: dq kernel S 2x64, dP 2x64, dS 2x32, dQ 64; dkv kernel S^T 2x64, dP^T 2x64, P^T 2x32, dS^T 2x32, dV 64, dK 64 (all 512).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (elect.sync), warps 2-9 compute: two warps per TMEM lane quarter,
-// each owning 64 of the 128 columns of its rows; the dS arithmetic runs as packed f32x2 FMA-pipe ops and the softmax scale
-// is applied once in the dQ / dK epilogue. The MMA and the compute phase of one tile still alternate (single-buffered
-// S / dP), so the tensor pipe idles while dS is computed.
+// i.e. two compute warpgroups. The streamed tiles are 64 rows and two are in flight: TMEM buffer b and warpgroup b serve the
+// tiles of parity b, so the MMAs of tile j+1 overlap the dS arithmetic of tile j (packed f32x2 FMA-pipe ops; the softmax
+// scale is applied once in the dQ / dK epilogue).
 #include "sm100.cuh"
 #include "attn_common.cuh"
 #include "../../include/videogpa_b200.h"
@@ -28,8 +28,6 @@ constexpr int AB_THREADS = 320;                             // TMA warp, MMA war
 constexpr int AB_T = 128;                                   // tile rows (queries or keys)
 constexpr int AB_D = 64;
 constexpr uint32_t AB_TILE = AB_T * AB_D * 2;               // 16384 bytes
-constexpr uint32_t AB_SMEM_DQ = 2 * AB_TILE + 2 * 2 * AB_TILE + 1024 + 256;            // Q, dO + 2 x (K, V)
-constexpr uint32_t AB_SMEM_DKV = 2 * AB_TILE + 2 * 2 * AB_TILE + 2 * 2 * AB_T * 4 + 1024 + 256;   // K, V + 2 x (Q, dO) + L/delta
 
 struct BwdParams {
   const float* lse;        // [B, H, Sq]
@@ -69,7 +67,14 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 }
 
 // ------------------------------------------------------------------------------------------------ dQ
+// kv tiles of AB_N = 64 rows, two in flight: TMEM buffer b (S 64 + dP 64 columns) and compute warpgroup b serve the tiles
+// j = b (mod 2), so the MMAs of tile j+1 run while warpgroup (j & 1) forms dS(j).
+constexpr int AB_N = 64;                                    // streamed tile rows
+constexpr uint32_t AB_TILE_N = AB_N * AB_D * 2;             // 8192 bytes
+constexpr int AB_SLOTS = 4;
+constexpr uint32_t AB_SMEM_BYTES = 2 * AB_TILE + AB_SLOTS * 2 * AB_TILE_N + 2 * 2 * AB_N * 4 * 2 + 1024 + 256;
 constexpr uint32_t DQ_COL_S = 0, DQ_COL_DP = 128, DQ_COL_DS = 256, DQ_COL_DQ = 320, DQ_TMEM_COLS = 512;
+//   S_b  [b*64, +64)   dP_b [128 + b*64, +64)   dS_b [256 + b*32, +32) (bf16 pairs)   dQ [320, +64)
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -78,27 +83,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + AB_TILE;
-  uint8_t* sKV = sdO + AB_TILE;                         // slot s: K at s * 2 tiles, V right after
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 4 * AB_TILE);
+  uint8_t* sKV = sdO + AB_TILE;                         // slot s: K at s * 2 small tiles, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AB_SLOTS * 2 * AB_TILE_N);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                         // [2]
-  uint64_t* kv_empty = bars + 3;                        // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* ds_ready = bars + 6;
-  uint64_t* dq_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;                         // [4]
+  uint64_t* kv_empty = bars + 5;                        // [4]
+  uint64_t* sdp_full = bars + 9;                        // [2]
+  uint64_t* ds_ready = bars + 11;                       // [2]
+  uint64_t* dq_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, batch = blockIdx.z;
   const int m0 = blockIdx.x * AB_T;
-  const int nkv = (prm.Skv + AB_T - 1) / AB_T;
+  const int nkv = (prm.Skv + AB_N - 1) / AB_N;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
     ptx::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
-    ptx::mbar_init(sdp_full, 1);
-    ptx::mbar_init(ds_ready, 256);
+    for (int i = 0; i < AB_SLOTS; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sdp_full[i], 1); ptx::mbar_init(&ds_ready[i], 128); }
     ptx::mbar_init(dq_done, 1);
     ptx::fence_barrier_init();
   }
@@ -117,51 +121,60 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::tma_load_3d(sQ, &tmQ, q_full, head * AB_D, m0, batch);
       ptx::tma_load_3d(sdO, &tmdO, q_full, head * AB_D, m0, batch);
       for (int j = 0; j < nkv; ++j) {
-        const int slot = j & 1;
-        ptx::mbar_wait(&kv_empty[slot], ((j >> 1) & 1) ^ 1);
-        ptx::mbar_expect_tx(&kv_full[slot], 2 * AB_TILE);
-        ptx::tma_load_3d(sKV + slot * 2 * AB_TILE, &tmK, &kv_full[slot], head * AB_D, j * AB_T, batch);
-        ptx::tma_load_3d(sKV + slot * 2 * AB_TILE + AB_TILE, &tmV, &kv_full[slot], head * AB_D, j * AB_T, batch);
+        const int slot = j % AB_SLOTS;
+        ptx::mbar_wait(&kv_empty[slot], ((j / AB_SLOTS) & 1) ^ 1);
+        ptx::mbar_expect_tx(&kv_full[slot], 2 * AB_TILE_N);
+        ptx::tma_load_3d(sKV + slot * 2 * AB_TILE_N, &tmK, &kv_full[slot], head * AB_D, j * AB_N, batch);
+        ptx::tma_load_3d(sKV + slot * 2 * AB_TILE_N + AB_TILE_N, &tmV, &kv_full[slot], head * AB_D, j * AB_N, batch);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    constexpr uint32_t idesc_s = ptx::idesc_bf16(AB_T, AB_T, 0, 0);     // [128 x 64] x [128 x 64]^T, both K-major
-    constexpr uint32_t idesc_o = ptx::idesc_bf16(AB_T, AB_D, 0, 1);     // TMEM [128 x 128] x tile [128 x 64] read MN-major
+    constexpr uint32_t idesc_s = ptx::idesc_bf16(AB_T, AB_N, 0, 0);     // [128 x 64 d] x [64 kv x 64 d]^T, both K-major
+    constexpr uint32_t idesc_o = ptx::idesc_bf16(AB_T, AB_D, 0, 1);     // TMEM [128 x 64 kv] x K tile [64 kv x 64 d] read MN-major
     const uint32_t sQ_a = ptx::smem_u32(sQ), sdO_a = ptx::smem_u32(sdO), sKV_a = ptx::smem_u32(sKV);
     if (ptx::elect_one()) {
+      auto issue_sdp = [&](int j) {
+        const int slot = j % AB_SLOTS, b = j & 1;
+        const uint32_t sK_a = sKV_a + slot * 2 * AB_TILE_N, sV_a = sK_a + AB_TILE_N;
+        ptx::mbar_wait(&kv_full[slot], (j / AB_SLOTS) & 1);
+        ptx::tc_fence_after();
+        {
+          const uint64_t a = ptx::smem_desc_sw128(sQ_a, 16, 1024), bd = ptx::smem_desc_sw128(sK_a, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + DQ_COL_S + b * AB_N, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        {
+          const uint64_t a = ptx::smem_desc_sw128(sdO_a, 16, 1024), bd = ptx::smem_desc_sw128(sV_a, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + DQ_COL_DP + b * AB_N, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&sdp_full[b]);
+      };
       ptx::mbar_wait(q_full, 0);
+      issue_sdp(0);
+      if (nkv > 1) issue_sdp(1);
       for (int j = 0; j < nkv; ++j) {
-        const int slot = j & 1;
-        const uint32_t sK_a = sKV_a + slot * 2 * AB_TILE, sV_a = sK_a + AB_TILE;
-        ptx::mbar_wait(&kv_full[slot], (j >> 1) & 1);
-        ptx::tc_fence_after();
-        {
-          const uint64_t a = ptx::smem_desc_sw128(sQ_a, 16, 1024), b = ptx::smem_desc_sw128(sK_a, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + DQ_COL_S, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        }
-        {
-          const uint64_t a = ptx::smem_desc_sw128(sdO_a, 16, 1024), b = ptx::smem_desc_sw128(sV_a, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + DQ_COL_DP, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        }
-        ptx::umma_commit(sdp_full);
-        ptx::mbar_wait(ds_ready, j & 1);
+        const int slot = j % AB_SLOTS, b = j & 1;
+        const uint32_t sK_a = sKV_a + slot * 2 * AB_TILE_N;
+        ptx::mbar_wait(&ds_ready[b], (j >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < AB_T / 16; ++kk) {
-          const uint64_t b = ptx::smem_desc_sw128(sK_a + kk * 2048, 1024, 1024);
-          ptx::umma_ts(tmem_base + DQ_COL_DQ, tmem_base + DQ_COL_DS + kk * 8, b, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < AB_N / 16; ++kk) {
+          const uint64_t bd = ptx::smem_desc_sw128(sK_a + kk * 2048, 1024, 1024);
+          ptx::umma_ts(tmem_base + DQ_COL_DQ, tmem_base + DQ_COL_DS + b * 32 + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         ptx::umma_commit(&kv_empty[slot]);
+        // S_b / dP_b were consumed before ds_ready[b]; dS_b is rewritten only after sdp_full[b] of tile j+2, which the
+        // in-order tensor pipe completes after the dQ MMAs above
+        if (j + 2 < nkv) issue_sdp(j + 2);
       }
       ptx::umma_commit(dq_done);
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;                         // which 64 of the 128 kv columns this warp handles
+    const int b = (warp - 2) >> 2;                            // warpgroup = TMEM buffer = parity of the kv tiles it serves
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int row = m0 + r;
@@ -170,17 +183,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float L = live ? prm.lse[stat] : INFINITY;          // rows past the end get P = 0
     const float dl = live ? prm.delta[stat] : 0.f;
     const uint64_t sc2 = f2_pack(prm.scale_log2, prm.scale_log2), negL2 = f2_pack(-L, -L), negdl2 = f2_pack(-dl, -dl);
-    const int tail = prm.Skv - (nkv - 1) * AB_T;
-    for (int j = 0; j < nkv; ++j) {
-      ptx::mbar_wait(sdp_full, j & 1);
+    const int tail = prm.Skv - (nkv - 1) * AB_N;
+    for (int j = b; j < nkv; j += 2) {
+      ptx::mbar_wait(&sdp_full[b], (j >> 1) & 1);
       ptx::tc_fence_after();
-      const int valid = (j == nkv - 1) ? tail : AB_T;
+      const int valid = (j == nkv - 1) ? tail : AB_N;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
+      for (int c = 0; c < 2; ++c) {
         uint32_t s[32], dp[32], pk[16];
-        ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_S + c * 32, s);
-        ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_DP + c * 32, dp);
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_S + b * AB_N + c * 32, s);
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_DP + b * AB_N + c * 32, dp);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -190,7 +202,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           f2_unpack(f2_mul(p2, f2_add(f2_pack(__uint_as_float(dp[2 * i]), __uint_as_float(dp[2 * i + 1])), negdl2)), d0, d1);
           pk[i] = pack_bf16x2(d0, d1);
         }
-        if (valid < AB_T) {                                   // last kv tile: columns past the end contribute nothing
+        if (valid < AB_N) {                                   // last kv tile: columns past the end contribute nothing
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int col = c * 32 + 2 * i;
@@ -198,18 +210,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             else if (col + 1 >= valid) pk[i] &= 0x0000ffffu;
           }
         }
-        ptx::tmem_st_32x16(tmem_base + lane_addr + DQ_COL_DS + c * 16, pk);
+        ptx::tmem_st_32x16(tmem_base + lane_addr + DQ_COL_DS + b * 32 + c * 16, pk);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(ds_ready);
+      ptx::mbar_arrive(&ds_ready[b]);
     }
     ptx::mbar_wait(dq_done, 0);
     ptx::tc_fence_after();
     __nv_bfloat16* dst = live ? prm.dq + static_cast<long long>(batch) * prm.dq_batch_stride +
                                     static_cast<long long>(row) * prm.dq_row_stride + head * AB_D
                               : nullptr;
-    store_cols(dst, tmem_base + lane_addr + DQ_COL_DQ, half * 2, half * 2 + 2, prm.scale);   // dS was formed without the scale
+    store_cols(dst, tmem_base + lane_addr + DQ_COL_DQ, b * 2, b * 2 + 2, prm.scale);   // dS was formed without the scale
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -217,8 +229,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
+// query tiles of 64 rows, two in flight (same ping-pong): per buffer S^T 64 + dP^T 64 + P^T 32 + dS^T 32 columns.
 constexpr uint32_t KV_COL_ST = 0, KV_COL_DPT = 128, KV_COL_PT = 256, KV_COL_DST = 320, KV_COL_DV = 384, KV_COL_DK = 448,
                    KV_TMEM_COLS = 512;
+//   S^T_b [b*64, +64)  dP^T_b [128 + b*64, +64)  P^T_b [256 + b*32, +32)  dS^T_b [320 + b*32, +32)  dV [384, +64)  dK [448, +64)
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -227,29 +241,28 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + AB_TILE;
-  uint8_t* sQdO = sV + AB_TILE;                         // slot s: Q at s * 2 tiles, dO right after
-  float* sL = reinterpret_cast<float*>(sQdO + 4 * AB_TILE);     // [2][128]
-  float* sDl = sL + 2 * AB_T;                                    // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * AB_T);
+  uint8_t* sQdO = sV + AB_TILE;                         // slot s: Q at s * 2 small tiles, dO right after
+  float* sL = reinterpret_cast<float*>(sQdO + AB_SLOTS * 2 * AB_TILE_N);     // [2 warpgroups][2][64]: -L
+  float* sDl = sL + 2 * 2 * AB_N;                                             // [2][2][64]: -delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * 2 * AB_N);
   uint64_t* kv_full = bars;
-  uint64_t* q_full = bars + 1;                          // [2]
-  uint64_t* q_empty = bars + 3;                         // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* ds_ready = bars + 6;
-  uint64_t* acc_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* q_full = bars + 1;                          // [4]
+  uint64_t* q_empty = bars + 5;                         // [4]
+  uint64_t* sdp_full = bars + 9;                        // [2]
+  uint64_t* ds_ready = bars + 11;                       // [2]
+  uint64_t* acc_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, batch = blockIdx.z;
   const int n0 = blockIdx.x * AB_T;
-  const int nq = (prm.Sq + AB_T - 1) / AB_T;
+  const int nq = (prm.Sq + AB_N - 1) / AB_N;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
     ptx::mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 1); }
-    ptx::mbar_init(sdp_full, 1);
-    ptx::mbar_init(ds_ready, 256);
+    for (int i = 0; i < AB_SLOTS; ++i) { ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sdp_full[i], 1); ptx::mbar_init(&ds_ready[i], 128); }
     ptx::mbar_init(acc_done, 1);
     ptx::fence_barrier_init();
   }
@@ -268,79 +281,85 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       ptx::tma_load_3d(sK, &tmK, kv_full, head * AB_D, n0, batch);
       ptx::tma_load_3d(sV, &tmV, kv_full, head * AB_D, n0, batch);
       for (int i = 0; i < nq; ++i) {
-        const int slot = i & 1;
-        ptx::mbar_wait(&q_empty[slot], ((i >> 1) & 1) ^ 1);
-        ptx::mbar_expect_tx(&q_full[slot], 2 * AB_TILE);
-        ptx::tma_load_3d(sQdO + slot * 2 * AB_TILE, &tmQ, &q_full[slot], head * AB_D, i * AB_T, batch);
-        ptx::tma_load_3d(sQdO + slot * 2 * AB_TILE + AB_TILE, &tmdO, &q_full[slot], head * AB_D, i * AB_T, batch);
+        const int slot = i % AB_SLOTS;
+        ptx::mbar_wait(&q_empty[slot], ((i / AB_SLOTS) & 1) ^ 1);
+        ptx::mbar_expect_tx(&q_full[slot], 2 * AB_TILE_N);
+        ptx::tma_load_3d(sQdO + slot * 2 * AB_TILE_N, &tmQ, &q_full[slot], head * AB_D, i * AB_N, batch);
+        ptx::tma_load_3d(sQdO + slot * 2 * AB_TILE_N + AB_TILE_N, &tmdO, &q_full[slot], head * AB_D, i * AB_N, batch);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    constexpr uint32_t idesc_s = ptx::idesc_bf16(AB_T, AB_T, 0, 0);
-    constexpr uint32_t idesc_o = ptx::idesc_bf16(AB_T, AB_D, 0, 1);
+    constexpr uint32_t idesc_s = ptx::idesc_bf16(AB_T, AB_N, 0, 0);     // K / V tile [128 x 64 d] x Q / dO tile [64 q x 64 d]^T
+    constexpr uint32_t idesc_o = ptx::idesc_bf16(AB_T, AB_D, 0, 1);     // TMEM [128 x 64 q] x dO / Q tile [64 q x 64 d] read MN-major
     const uint32_t sK_a = ptx::smem_u32(sK), sV_a = ptx::smem_u32(sV), sQdO_a = ptx::smem_u32(sQdO);
     if (ptx::elect_one()) {
+      auto issue_sdp = [&](int i) {
+        const int slot = i % AB_SLOTS, b = i & 1;
+        const uint32_t sQ_a = sQdO_a + slot * 2 * AB_TILE_N, sdO_a = sQ_a + AB_TILE_N;
+        ptx::mbar_wait(&q_full[slot], (i / AB_SLOTS) & 1);
+        ptx::tc_fence_after();
+        {
+          const uint64_t a = ptx::smem_desc_sw128(sK_a, 16, 1024), bd = ptx::smem_desc_sw128(sQ_a, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + KV_COL_ST + b * AB_N, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        {
+          const uint64_t a = ptx::smem_desc_sw128(sV_a, 16, 1024), bd = ptx::smem_desc_sw128(sdO_a, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + KV_COL_DPT + b * AB_N, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&sdp_full[b]);
+      };
       ptx::mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      if (nq > 1) issue_sdp(1);
       for (int i = 0; i < nq; ++i) {
-        const int slot = i & 1;
-        const uint32_t sQ_a = sQdO_a + slot * 2 * AB_TILE, sdO_a = sQ_a + AB_TILE;
-        ptx::mbar_wait(&q_full[slot], (i >> 1) & 1);
-        ptx::tc_fence_after();
-        {
-          const uint64_t a = ptx::smem_desc_sw128(sK_a, 16, 1024), b = ptx::smem_desc_sw128(sQ_a, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + KV_COL_ST, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        }
-        {
-          const uint64_t a = ptx::smem_desc_sw128(sV_a, 16, 1024), b = ptx::smem_desc_sw128(sdO_a, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + KV_COL_DPT, a + 2 * k, b + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        }
-        ptx::umma_commit(sdp_full);
-        ptx::mbar_wait(ds_ready, i & 1);
+        const int slot = i % AB_SLOTS, b = i & 1;
+        const uint32_t sQ_a = sQdO_a + slot * 2 * AB_TILE_N, sdO_a = sQ_a + AB_TILE_N;
+        ptx::mbar_wait(&ds_ready[b], (i >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < AB_T / 16; ++kk) {
-          const uint64_t b = ptx::smem_desc_sw128(sdO_a + kk * 2048, 1024, 1024);
-          ptx::umma_ts(tmem_base + KV_COL_DV, tmem_base + KV_COL_PT + kk * 8, b, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < AB_N / 16; ++kk) {
+          const uint64_t bd = ptx::smem_desc_sw128(sdO_a + kk * 2048, 1024, 1024);
+          ptx::umma_ts(tmem_base + KV_COL_DV, tmem_base + KV_COL_PT + b * 32 + kk * 8, bd, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
         }
 #pragma unroll
-        for (int kk = 0; kk < AB_T / 16; ++kk) {
-          const uint64_t b = ptx::smem_desc_sw128(sQ_a + kk * 2048, 1024, 1024);
-          ptx::umma_ts(tmem_base + KV_COL_DK, tmem_base + KV_COL_DST + kk * 8, b, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < AB_N / 16; ++kk) {
+          const uint64_t bd = ptx::smem_desc_sw128(sQ_a + kk * 2048, 1024, 1024);
+          ptx::umma_ts(tmem_base + KV_COL_DK, tmem_base + KV_COL_DST + b * 32 + kk * 8, bd, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
         }
         ptx::umma_commit(&q_empty[slot]);
+        if (i + 2 < nq) issue_sdp(i + 2);
       }
       ptx::umma_commit(acc_done);
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;                         // which 64 of the 128 query columns this warp handles
+    const int b = (warp - 2) >> 2;                            // warpgroup = TMEM buffer = parity of the query tiles it serves
     const int r = quarter * 32 + lane;                        // key row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const long long stat0 = (static_cast<long long>(batch) * prm.H + head) * prm.Sq;
     const uint64_t sc2 = f2_pack(prm.scale_log2, prm.scale_log2);
-    for (int i = 0; i < nq; ++i) {
-      const int slot = i & 1;
-      if (half == 0) {                                        // -L and -delta of the tile's 128 queries
-        const int q = i * AB_T + r;
+    for (int i = b; i < nq; i += 2) {
+      const int buf = (i >> 1) & 1;
+      float* Lq = sL + (b * 2 + buf) * AB_N;
+      float* Dq = sDl + (b * 2 + buf) * AB_N;
+      if (r < AB_N) {                                         // -L and -delta of the tile's 64 queries
+        const int q = i * AB_N + r;
         const bool ok = q < prm.Sq;
-        sL[slot * AB_T + r] = ok ? -prm.lse[stat0 + q] : -INFINITY;    // queries past the end: P = 0
-        sDl[slot * AB_T + r] = ok ? -prm.delta[stat0 + q] : 0.f;
+        Lq[r] = ok ? -prm.lse[stat0 + q] : -INFINITY;         // queries past the end: P = 0
+        Dq[r] = ok ? -prm.delta[stat0 + q] : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      ptx::mbar_wait(sdp_full, i & 1);
+      if (b == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      ptx::mbar_wait(&sdp_full[b], (i >> 1) & 1);
       ptx::tc_fence_after();
-      const float* Lq = sL + slot * AB_T;
-      const float* Dq = sDl + slot * AB_T;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
+      for (int c = 0; c < 2; ++c) {
         uint32_t s[32], dp[32], pp[16], pd[16];
-        ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_ST + c * 32, s);
-        ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_DPT + c * 32, dp);
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_ST + b * AB_N + c * 32, s);
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_DPT + b * AB_N + c * 32, dp);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -354,12 +373,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pp[k] = pack_bf16x2(p0, p1);
           pd[k] = pack_bf16x2(d0, d1);
         }
-        ptx::tmem_st_32x16(tmem_base + lane_addr + KV_COL_PT + c * 16, pp);
-        ptx::tmem_st_32x16(tmem_base + lane_addr + KV_COL_DST + c * 16, pd);
+        ptx::tmem_st_32x16(tmem_base + lane_addr + KV_COL_PT + b * 32 + c * 16, pp);
+        ptx::tmem_st_32x16(tmem_base + lane_addr + KV_COL_DST + b * 32 + c * 16, pd);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(ds_ready);
+      ptx::mbar_arrive(&ds_ready[b]);
     }
     ptx::mbar_wait(acc_done, 0);
     ptx::tc_fence_after();
@@ -369,8 +388,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                     static_cast<long long>(row) * prm.dv_row_stride + head * AB_D : nullptr;
     __nv_bfloat16* dkp = live ? prm.dk + static_cast<long long>(batch) * prm.dk_batch_stride +
                                     static_cast<long long>(row) * prm.dk_row_stride + head * AB_D : nullptr;
-    store_cols(dvp, tmem_base + lane_addr + KV_COL_DV, half * 2, half * 2 + 2, 1.0f);
-    store_cols(dkp, tmem_base + lane_addr + KV_COL_DK, half * 2, half * 2 + 2, prm.scale);      // dS^T was formed without the scale
+    store_cols(dvp, tmem_base + lane_addr + KV_COL_DV, b * 2, b * 2 + 2, 1.0f);
+    store_cols(dkp, tmem_base + lane_addr + KV_COL_DK, b * 2, b * 2 + 2, prm.scale);      // dS^T was formed without the scale
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -442,17 +461,21 @@ extern "C" int vgpa_attention_bwd_bf16(const vgpa_attention_bwd_args* a, void* s
         a->out_row_stride, a->out_batch_stride, a->dout_row_stride, a->dout_batch_stride);
     VGPA_LAUNCH_CHECK("attn_delta_kernel");
   }
-  CUtensorMap tq, tk, tv, tdo;
-  const uint32_t box[3] = {64, 128, 1};
-  auto mk = [&](CUtensorMap* tm, const void* p, int S, int64_t row, int64_t batch) {
+  CUtensorMap tq, tk, tv, tdo, tq_n, tk_n, tv_n, tdo_n;      // 128-row boxes (resident tiles) and 64-row boxes (streamed tiles)
+  auto mk = [&](CUtensorMap* tm, const void* p, int S, int64_t row, int64_t batch, uint32_t box_rows) {
+    const uint32_t box[3] = {64, box_rows, 1};
     const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)S, (uint64_t)a->B};
     const uint64_t str[2] = {(uint64_t)row * 2, (uint64_t)batch * 2};
     return make_tmap_bf16(tm, p, 3, dims, str, box);
   };
-  if (int rc = mk(&tq, a->q, a->Sq, a->q_row_stride, a->q_batch_stride)) return rc;
-  if (int rc = mk(&tk, a->k, a->Skv, a->k_row_stride, a->k_batch_stride)) return rc;
-  if (int rc = mk(&tv, a->v, a->Skv, a->v_row_stride, a->v_batch_stride)) return rc;
-  if (int rc = mk(&tdo, a->d_out, a->Sq, a->dout_row_stride, a->dout_batch_stride)) return rc;
+  if (int rc = mk(&tq, a->q, a->Sq, a->q_row_stride, a->q_batch_stride, 128)) return rc;
+  if (int rc = mk(&tk, a->k, a->Skv, a->k_row_stride, a->k_batch_stride, 128)) return rc;
+  if (int rc = mk(&tv, a->v, a->Skv, a->v_row_stride, a->v_batch_stride, 128)) return rc;
+  if (int rc = mk(&tdo, a->d_out, a->Sq, a->dout_row_stride, a->dout_batch_stride, 128)) return rc;
+  if (int rc = mk(&tq_n, a->q, a->Sq, a->q_row_stride, a->q_batch_stride, 64)) return rc;
+  if (int rc = mk(&tk_n, a->k, a->Skv, a->k_row_stride, a->k_batch_stride, 64)) return rc;
+  if (int rc = mk(&tv_n, a->v, a->Skv, a->v_row_stride, a->v_batch_stride, 64)) return rc;
+  if (int rc = mk(&tdo_n, a->d_out, a->Sq, a->dout_row_stride, a->dout_batch_stride, 64)) return rc;
   BwdParams prm;
   prm.lse = a->lse; prm.delta = delta;
   prm.dq = static_cast<__nv_bfloat16*>(a->dq); prm.dk = static_cast<__nv_bfloat16*>(a->dk); prm.dv = static_cast<__nv_bfloat16*>(a->dv);
@@ -464,13 +487,13 @@ extern "C" int vgpa_attention_bwd_bf16(const vgpa_attention_bwd_args* a, void* s
   prm.scale_log2 = prm.scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    VGPA_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_DQ));
-    VGPA_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_DKV));
+    VGPA_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    VGPA_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
     attr_set = true;
   }
-  attn_bwd_dq_kernel<<<dim3((a->Sq + AB_T - 1) / AB_T, a->H, a->B), AB_THREADS, AB_SMEM_DQ, s>>>(tq, tk, tv, tdo, prm);
+  attn_bwd_dq_kernel<<<dim3((a->Sq + AB_T - 1) / AB_T, a->H, a->B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk_n, tv_n, tdo, prm);
   VGPA_LAUNCH_CHECK("attn_bwd_dq_kernel");
-  attn_bwd_dkv_kernel<<<dim3((a->Skv + AB_T - 1) / AB_T, a->H, a->B), AB_THREADS, AB_SMEM_DKV, s>>>(tq, tk, tv, tdo, prm);
+  attn_bwd_dkv_kernel<<<dim3((a->Skv + AB_T - 1) / AB_T, a->H, a->B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq_n, tk, tv, tdo_n, prm);
   VGPA_LAUNCH_CHECK("attn_bwd_dkv_kernel");
   return 0;
 }
