@@ -11,10 +11,10 @@
 //   * attn_bwd_dkv_kernel: one CTA per (128-key tile, head, sample), loops over query tiles, transposed problem:
 //       S^T = K Q^T, dP^T = V dO^T -> TMEM; threads own key rows, L / delta of the 128 queries come from shared memory;
 //       dV += P^T dO_i and dK += dS^T Q_i are TS MMAs with the dO / Q tiles read MN-major.
-// TMEM: dq kernel S 2x64, dP 2x64, dS 2x32, dQ 64; dkv kernel S^T 2x64, dP^T 2x64, P^T 2x32, dS^T 2x32, dV 64, dK 64 (all 512).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (elect.sync), warps 2-9 compute: two warps per TMEM lane quarter,
-// i.e. two compute warpgroups. The streamed tiles are 64 rows and two are in flight: TMEM buffer b and warpgroup b serve the
-// tiles of parity b, so the MMAs of tile j+1 overlap the dS arithmetic of tile j (packed f32x2 FMA-pipe ops; the softmax
+// TMEM: 3 buffers of 128 columns (S | dP, the bf16 dS / P^T / dS^T written in place over consumed columns) + dQ 64, or dV 64 + dK 64.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (elect.sync), warps 2-13 compute: three warps per TMEM lane quarter,
+// i.e. three compute warpgroups. The streamed tiles are 64 rows and three are in flight: TMEM buffer b and warpgroup b serve
+// the tiles j = b (mod 3), so the MMAs of the next tiles overlap the dS arithmetic of tile j (packed f32x2 FMA-pipe ops; the softmax
 // scale is applied once in the dQ / dK epilogue).
 #include "sm100.cuh"
 #include "attn_common.cuh"
@@ -24,7 +24,8 @@
 namespace vgpa {
 namespace {
 
-constexpr int AB_THREADS = 320;                             // TMA warp, MMA warp, 2 x 4 compute warps
+constexpr int AB_NBUF = 3;                                  // TMEM buffers = compute warpgroups = streamed tiles in flight
+constexpr int AB_THREADS = 64 + AB_NBUF * 128;              // TMA warp, MMA warp, AB_NBUF x 4 compute warps
 constexpr int AB_T = 128;                                   // tile rows (queries or keys)
 constexpr int AB_D = 64;
 constexpr uint32_t AB_TILE = AB_T * AB_D * 2;               // 16384 bytes
@@ -71,10 +72,11 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 // j = b (mod 2), so the MMAs of tile j+1 run while warpgroup (j & 1) forms dS(j).
 constexpr int AB_N = 64;                                    // streamed tile rows
 constexpr uint32_t AB_TILE_N = AB_N * AB_D * 2;             // 8192 bytes
-constexpr int AB_SLOTS = 4;
-constexpr uint32_t AB_SMEM_BYTES = 2 * AB_TILE + AB_SLOTS * 2 * AB_TILE_N + 2 * 2 * AB_N * 4 * 2 + 1024 + 256;
-constexpr uint32_t DQ_COL_S = 0, DQ_COL_DP = 128, DQ_COL_DS = 256, DQ_COL_DQ = 320, DQ_TMEM_COLS = 512;
-//   S_b  [b*64, +64)   dP_b [128 + b*64, +64)   dS_b [256 + b*32, +32) (bf16 pairs)   dQ [320, +64)
+constexpr int AB_SLOTS = 6;
+constexpr uint32_t AB_SMEM_BYTES = 2 * AB_TILE + AB_SLOTS * 2 * AB_TILE_N + AB_NBUF * 2 * AB_N * 4 * 2 + 1024 + 256;
+constexpr uint32_t DQ_BUF = 128, DQ_COL_DP = 64, DQ_COL_DQ = AB_NBUF * DQ_BUF, DQ_TMEM_COLS = 512;
+//   buffer b at b*128: S_b [0, 64), dP_b [64, 128); dS_b (bf16 pairs, 32 columns) overwrites S_b in place: a thread
+//   stores the 16 columns of chunk c only after it has loaded S columns [32c, 32c+32), which cover them.   dQ [384, +64)
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -86,12 +88,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sKV = sdO + AB_TILE;                         // slot s: K at s * 2 small tiles, V right after
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AB_SLOTS * 2 * AB_TILE_N);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                         // [4]
-  uint64_t* kv_empty = bars + 5;                        // [4]
-  uint64_t* sdp_full = bars + 9;                        // [2]
-  uint64_t* ds_ready = bars + 11;                       // [2]
-  uint64_t* dq_done = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* kv_full = bars + 1;                         // [AB_SLOTS]
+  uint64_t* kv_empty = kv_full + AB_SLOTS;              // [AB_SLOTS]
+  uint64_t* sdp_full = kv_empty + AB_SLOTS;             // [AB_NBUF]
+  uint64_t* ds_ready = sdp_full + AB_NBUF;              // [AB_NBUF]
+  uint64_t* dq_done = ds_ready + AB_NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, batch = blockIdx.z;
@@ -102,7 +104,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
     ptx::mbar_init(q_full, 1);
     for (int i = 0; i < AB_SLOTS; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sdp_full[i], 1); ptx::mbar_init(&ds_ready[i], 128); }
+    for (int i = 0; i < AB_NBUF; ++i) { ptx::mbar_init(&sdp_full[i], 1); ptx::mbar_init(&ds_ready[i], 128); }
     ptx::mbar_init(dq_done, 1);
     ptx::fence_barrier_init();
   }
@@ -135,46 +137,45 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t sQ_a = ptx::smem_u32(sQ), sdO_a = ptx::smem_u32(sdO), sKV_a = ptx::smem_u32(sKV);
     if (ptx::elect_one()) {
       auto issue_sdp = [&](int j) {
-        const int slot = j % AB_SLOTS, b = j & 1;
+        const int slot = j % AB_SLOTS, b = j % AB_NBUF;
         const uint32_t sK_a = sKV_a + slot * 2 * AB_TILE_N, sV_a = sK_a + AB_TILE_N;
         ptx::mbar_wait(&kv_full[slot], (j / AB_SLOTS) & 1);
         ptx::tc_fence_after();
         {
           const uint64_t a = ptx::smem_desc_sw128(sQ_a, 16, 1024), bd = ptx::smem_desc_sw128(sK_a, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + DQ_COL_S + b * AB_N, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + b * DQ_BUF, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         }
         {
           const uint64_t a = ptx::smem_desc_sw128(sdO_a, 16, 1024), bd = ptx::smem_desc_sw128(sV_a, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + DQ_COL_DP + b * AB_N, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + b * DQ_BUF + DQ_COL_DP, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         }
         ptx::umma_commit(&sdp_full[b]);
       };
       ptx::mbar_wait(q_full, 0);
-      issue_sdp(0);
-      if (nkv > 1) issue_sdp(1);
+      for (int j = 0; j < AB_NBUF && j < nkv; ++j) issue_sdp(j);
       for (int j = 0; j < nkv; ++j) {
-        const int slot = j % AB_SLOTS, b = j & 1;
+        const int slot = j % AB_SLOTS, b = j % AB_NBUF;
         const uint32_t sK_a = sKV_a + slot * 2 * AB_TILE_N;
-        ptx::mbar_wait(&ds_ready[b], (j >> 1) & 1);
+        ptx::mbar_wait(&ds_ready[b], (j / AB_NBUF) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < AB_N / 16; ++kk) {
           const uint64_t bd = ptx::smem_desc_sw128(sK_a + kk * 2048, 1024, 1024);
-          ptx::umma_ts(tmem_base + DQ_COL_DQ, tmem_base + DQ_COL_DS + b * 32 + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          ptx::umma_ts(tmem_base + DQ_COL_DQ, tmem_base + b * DQ_BUF + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         ptx::umma_commit(&kv_empty[slot]);
-        // S_b / dP_b were consumed before ds_ready[b]; dS_b is rewritten only after sdp_full[b] of tile j+2, which the
-        // in-order tensor pipe completes after the dQ MMAs above
-        if (j + 2 < nkv) issue_sdp(j + 2);
+        // buffer b (S / dP, and dS in place of S) is rewritten by the MMAs of tile j + AB_NBUF, which the in-order tensor
+        // pipe runs after the dQ MMAs above have read dS_b
+        if (j + AB_NBUF < nkv) issue_sdp(j + AB_NBUF);
       }
       ptx::umma_commit(dq_done);
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    const int b = (warp - 2) >> 2;                            // warpgroup = TMEM buffer = parity of the kv tiles it serves
+    const int b = (warp - 2) >> 2;                            // warpgroup = TMEM buffer; serves the kv tiles j = b (mod AB_NBUF)
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int row = m0 + r;
@@ -184,15 +185,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float dl = live ? prm.delta[stat] : 0.f;
     const uint64_t sc2 = f2_pack(prm.scale_log2, prm.scale_log2), negL2 = f2_pack(-L, -L), negdl2 = f2_pack(-dl, -dl);
     const int tail = prm.Skv - (nkv - 1) * AB_N;
-    for (int j = b; j < nkv; j += 2) {
-      ptx::mbar_wait(&sdp_full[b], (j >> 1) & 1);
+    const uint32_t tbuf = tmem_base + lane_addr + b * DQ_BUF;
+    for (int j = b; j < nkv; j += AB_NBUF) {
+      ptx::mbar_wait(&sdp_full[b], (j / AB_NBUF) & 1);
       ptx::tc_fence_after();
       const int valid = (j == nkv - 1) ? tail : AB_N;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t s[32], dp[32], pk[16];
-        ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_S + b * AB_N + c * 32, s);
-        ptx::tmem_ld_32x32(tmem_base + lane_addr + DQ_COL_DP + b * AB_N + c * 32, dp);
+        ptx::tmem_ld_32x32(tbuf + c * 32, s);
+        ptx::tmem_ld_32x32(tbuf + DQ_COL_DP + c * 32, dp);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -210,7 +212,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             else if (col + 1 >= valid) pk[i] &= 0x0000ffffu;
           }
         }
-        ptx::tmem_st_32x16(tmem_base + lane_addr + DQ_COL_DS + b * 32 + c * 16, pk);
+        ptx::tmem_st_32x16(tbuf + c * 16, pk);                // dS over the S columns this thread has already consumed
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -221,7 +223,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __nv_bfloat16* dst = live ? prm.dq + static_cast<long long>(batch) * prm.dq_batch_stride +
                                     static_cast<long long>(row) * prm.dq_row_stride + head * AB_D
                               : nullptr;
-    store_cols(dst, tmem_base + lane_addr + DQ_COL_DQ, b * 2, b * 2 + 2, prm.scale);   // dS was formed without the scale
+    // dS was formed without the scale; the 4 column chunks are split over the warpgroups (0: chunks 0-1, 1: chunk 2, 2: chunk 3)
+    store_cols(dst, tmem_base + lane_addr + DQ_COL_DQ, b == 0 ? 0 : b + 1, b == 0 ? 2 : b + 2, prm.scale);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -230,9 +233,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 // ------------------------------------------------------------------------------------------------ dK, dV
 // query tiles of 64 rows, two in flight (same ping-pong): per buffer S^T 64 + dP^T 64 + P^T 32 + dS^T 32 columns.
-constexpr uint32_t KV_COL_ST = 0, KV_COL_DPT = 128, KV_COL_PT = 256, KV_COL_DST = 320, KV_COL_DV = 384, KV_COL_DK = 448,
-                   KV_TMEM_COLS = 512;
-//   S^T_b [b*64, +64)  dP^T_b [128 + b*64, +64)  P^T_b [256 + b*32, +32)  dS^T_b [320 + b*32, +32)  dV [384, +64)  dK [448, +64)
+constexpr uint32_t KV_BUF = 128, KV_COL_DPT = 64, KV_COL_DV = AB_NBUF * KV_BUF, KV_COL_DK = KV_COL_DV + 64, KV_TMEM_COLS = 512;
+//   buffer b at b*128: S^T_b [0, 64), dP^T_b [64, 128); P^T_b (bf16 pairs) overwrites S^T_b and dS^T_b overwrites dP^T_b in
+//   place, 8 columns per 16-column chunk already loaded by the same thread.   dV [384, +64)   dK [448, +64)
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -242,16 +245,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = smem;
   uint8_t* sV = sK + AB_TILE;
   uint8_t* sQdO = sV + AB_TILE;                         // slot s: Q at s * 2 small tiles, dO right after
-  float* sL = reinterpret_cast<float*>(sQdO + AB_SLOTS * 2 * AB_TILE_N);     // [2 warpgroups][2][64]: -L
-  float* sDl = sL + 2 * 2 * AB_N;                                             // [2][2][64]: -delta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * 2 * AB_N);
+  float* sL = reinterpret_cast<float*>(sQdO + AB_SLOTS * 2 * AB_TILE_N);     // [warpgroup][2][64]: -L
+  float* sDl = sL + AB_NBUF * 2 * AB_N;                                       // [warpgroup][2][64]: -delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + AB_NBUF * 2 * AB_N);
   uint64_t* kv_full = bars;
-  uint64_t* q_full = bars + 1;                          // [4]
-  uint64_t* q_empty = bars + 5;                         // [4]
-  uint64_t* sdp_full = bars + 9;                        // [2]
-  uint64_t* ds_ready = bars + 11;                       // [2]
-  uint64_t* acc_done = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_full = bars + 1;                          // [AB_SLOTS]
+  uint64_t* q_empty = q_full + AB_SLOTS;                // [AB_SLOTS]
+  uint64_t* sdp_full = q_empty + AB_SLOTS;              // [AB_NBUF]
+  uint64_t* ds_ready = sdp_full + AB_NBUF;              // [AB_NBUF]
+  uint64_t* acc_done = ds_ready + AB_NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, batch = blockIdx.z;
@@ -262,7 +265,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmdO);
     ptx::mbar_init(kv_full, 1);
     for (int i = 0; i < AB_SLOTS; ++i) { ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sdp_full[i], 1); ptx::mbar_init(&ds_ready[i], 128); }
+    for (int i = 0; i < AB_NBUF; ++i) { ptx::mbar_init(&sdp_full[i], 1); ptx::mbar_init(&ds_ready[i], 128); }
     ptx::mbar_init(acc_done, 1);
     ptx::fence_barrier_init();
   }
@@ -295,75 +298,74 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t sK_a = ptx::smem_u32(sK), sV_a = ptx::smem_u32(sV), sQdO_a = ptx::smem_u32(sQdO);
     if (ptx::elect_one()) {
       auto issue_sdp = [&](int i) {
-        const int slot = i % AB_SLOTS, b = i & 1;
+        const int slot = i % AB_SLOTS, b = i % AB_NBUF;
         const uint32_t sQ_a = sQdO_a + slot * 2 * AB_TILE_N, sdO_a = sQ_a + AB_TILE_N;
         ptx::mbar_wait(&q_full[slot], (i / AB_SLOTS) & 1);
         ptx::tc_fence_after();
         {
           const uint64_t a = ptx::smem_desc_sw128(sK_a, 16, 1024), bd = ptx::smem_desc_sw128(sQ_a, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + KV_COL_ST + b * AB_N, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + b * KV_BUF, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         }
         {
           const uint64_t a = ptx::smem_desc_sw128(sV_a, 16, 1024), bd = ptx::smem_desc_sw128(sdO_a, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + KV_COL_DPT + b * AB_N, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < AB_D / 16; ++k) ptx::umma_ss(tmem_base + b * KV_BUF + KV_COL_DPT, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         }
         ptx::umma_commit(&sdp_full[b]);
       };
       ptx::mbar_wait(kv_full, 0);
-      issue_sdp(0);
-      if (nq > 1) issue_sdp(1);
+      for (int i = 0; i < AB_NBUF && i < nq; ++i) issue_sdp(i);
       for (int i = 0; i < nq; ++i) {
-        const int slot = i % AB_SLOTS, b = i & 1;
+        const int slot = i % AB_SLOTS, b = i % AB_NBUF;
         const uint32_t sQ_a = sQdO_a + slot * 2 * AB_TILE_N, sdO_a = sQ_a + AB_TILE_N;
-        ptx::mbar_wait(&ds_ready[b], (i >> 1) & 1);
+        ptx::mbar_wait(&ds_ready[b], (i / AB_NBUF) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < AB_N / 16; ++kk) {
           const uint64_t bd = ptx::smem_desc_sw128(sdO_a + kk * 2048, 1024, 1024);
-          ptx::umma_ts(tmem_base + KV_COL_DV, tmem_base + KV_COL_PT + b * 32 + kk * 8, bd, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+          ptx::umma_ts(tmem_base + KV_COL_DV, tmem_base + b * KV_BUF + kk * 8, bd, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < AB_N / 16; ++kk) {
           const uint64_t bd = ptx::smem_desc_sw128(sQ_a + kk * 2048, 1024, 1024);
-          ptx::umma_ts(tmem_base + KV_COL_DK, tmem_base + KV_COL_DST + b * 32 + kk * 8, bd, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
+          ptx::umma_ts(tmem_base + KV_COL_DK, tmem_base + b * KV_BUF + KV_COL_DPT + kk * 8, bd, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
         }
         ptx::umma_commit(&q_empty[slot]);
-        if (i + 2 < nq) issue_sdp(i + 2);
+        if (i + AB_NBUF < nq) issue_sdp(i + AB_NBUF);
       }
       ptx::umma_commit(acc_done);
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    const int b = (warp - 2) >> 2;                            // warpgroup = TMEM buffer = parity of the query tiles it serves
+    const int b = (warp - 2) >> 2;                            // warpgroup = TMEM buffer; serves the query tiles i = b (mod AB_NBUF)
     const int r = quarter * 32 + lane;                        // key row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const long long stat0 = (static_cast<long long>(batch) * prm.H + head) * prm.Sq;
     const uint64_t sc2 = f2_pack(prm.scale_log2, prm.scale_log2);
-    for (int i = b; i < nq; i += 2) {
-      const int buf = (i >> 1) & 1;
-      float* Lq = sL + (b * 2 + buf) * AB_N;
-      float* Dq = sDl + (b * 2 + buf) * AB_N;
+    const uint32_t tbuf = tmem_base + lane_addr + b * KV_BUF;
+    for (int i = b, n = 0; i < nq; i += AB_NBUF, ++n) {
+      float* Lq = sL + (b * 2 + (n & 1)) * AB_N;
+      float* Dq = sDl + (b * 2 + (n & 1)) * AB_N;
       if (r < AB_N) {                                         // -L and -delta of the tile's 64 queries
         const int q = i * AB_N + r;
         const bool ok = q < prm.Sq;
         Lq[r] = ok ? -prm.lse[stat0 + q] : -INFINITY;         // queries past the end: P = 0
         Dq[r] = ok ? -prm.delta[stat0 + q] : 0.f;
       }
-      if (b == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-      ptx::mbar_wait(&sdp_full[b], (i >> 1) & 1);
+      asm volatile("bar.sync %0, 128;" ::"r"(b + 1) : "memory");
+      ptx::mbar_wait(&sdp_full[b], n & 1);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t s[32], dp[32], pp[16], pd[16];
-        ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_ST + b * AB_N + c * 32, s);
-        ptx::tmem_ld_32x32(tmem_base + lane_addr + KV_COL_DPT + b * AB_N + c * 32, dp);
+      for (int c = 0; c < 4; ++c) {                           // 16 query columns at a time
+        uint32_t s[16], dp[16], pp[8], pd[8];
+        ptx::tmem_ld_32x16(tbuf + c * 16, s);
+        ptx::tmem_ld_32x16(tbuf + KV_COL_DPT + c * 16, dp);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int q0 = c * 32 + 2 * k;
+        for (int k = 0; k < 8; ++k) {
+          const int q0 = c * 16 + 2 * k;
           const uint64_t negL2 = *reinterpret_cast<const uint64_t*>(Lq + q0);
           const uint64_t negdl2 = *reinterpret_cast<const uint64_t*>(Dq + q0);
           float x0, x1, d0, d1;
@@ -373,8 +375,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pp[k] = pack_bf16x2(p0, p1);
           pd[k] = pack_bf16x2(d0, d1);
         }
-        ptx::tmem_st_32x16(tmem_base + lane_addr + KV_COL_PT + b * 32 + c * 16, pp);
-        ptx::tmem_st_32x16(tmem_base + lane_addr + KV_COL_DST + b * 32 + c * 16, pd);
+        ptx::tmem_st_32x8(tbuf + c * 8, pp);                  // P^T over consumed S^T columns, dS^T over consumed dP^T columns
+        ptx::tmem_st_32x8(tbuf + KV_COL_DPT + c * 8, pd);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -388,8 +390,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                     static_cast<long long>(row) * prm.dv_row_stride + head * AB_D : nullptr;
     __nv_bfloat16* dkp = live ? prm.dk + static_cast<long long>(batch) * prm.dk_batch_stride +
                                     static_cast<long long>(row) * prm.dk_row_stride + head * AB_D : nullptr;
-    store_cols(dvp, tmem_base + lane_addr + KV_COL_DV, b * 2, b * 2 + 2, 1.0f);
-    store_cols(dkp, tmem_base + lane_addr + KV_COL_DK, b * 2, b * 2 + 2, prm.scale);      // dS^T was formed without the scale
+    const int cb = b == 0 ? 0 : b + 1, ce = b == 0 ? 2 : b + 2;   // 4 column chunks over the warpgroups: 0-1, 2, 3
+    store_cols(dvp, tmem_base + lane_addr + KV_COL_DV, cb, ce, 1.0f);
+    store_cols(dkp, tmem_base + lane_addr + KV_COL_DK, cb, ce, prm.scale);               // dS^T was formed without the scale
   }
   ptx::tc_fence_before();
   __syncthreads();
