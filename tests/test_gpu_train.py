@@ -221,6 +221,17 @@ def test_dpo_training_step_gradients_vs_oracle_autograd(lib):
     for layer in range(2):
         for m in TARGETS:
             assert torch.equal(pol2.lora[layer][m][0].grad, pol.lora[layer][m][0].grad)
+    # ... nor does recomputing only the MLP half
+    pol3 = LoRATrainableTransformer(base, r=64, lora_alpha=128.0, seed=3, gradient_checkpointing="mlp")
+    for layer in range(2):
+        for m in TARGETS:
+            with torch.no_grad():
+                pol3.lora[layer][m][0].copy_(pol.lora[layer][m][0])
+                pol3.lora[layer][m][1].copy_(pol.lora[layer][m][1])
+    DPOSharedStep(base, None, beta=beta, trainable=pol3).training_step(batch, timesteps=t.cuda(), noise=noise.cuda()).backward()
+    for layer in range(2):
+        for m in TARGETS:
+            assert torch.equal(pol3.lora[layer][m][1].grad, pol.lora[layer][m][1].grad)
     # one optimizer step (AdamW, lr 5e-6 as in 03_train.py:207-210) moves every factor
     opt = step.configure_optimizers()
     before = pol.lora[1]["to_q"][0].detach().clone()

@@ -9,7 +9,9 @@ from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
 L = int(os.environ.get("LAYERS", "42"))
 cfg = TransformerConfig.cogvideox_5b(); cfg.num_layers = L
 base = CogVideoXTransformer3D.random_init(cfg, seed=1234, device="cuda")
-pol = LoRATrainableTransformer(base, r=64, lora_alpha=128.0)
+ck = {"full": True, "mlp": "mlp", "none": False}[os.environ.get("CKPT", "full")]
+pol = LoRATrainableTransformer(base, r=64, lora_alpha=128.0, gradient_checkpointing=ck)
+print("checkpointing:", ck)
 step = DPOSharedStep(base, None, beta=1.0, trainable=pol)
 opt = step.configure_optimizers()
 g = torch.Generator().manual_seed(0)

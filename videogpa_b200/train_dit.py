@@ -215,7 +215,13 @@ class LoRATrainableTransformer:
     """`get_peft_model(transformer, LoraConfig(r, lora_alpha, target_modules=[to_q, to_k, to_v, to_out.0]))` for the sm_100a DiT:
     wraps a CogVideoXTransformer3D (frozen, shared), owns the fp32 LoRA factors and runs the differentiable forward."""
 
-    def __init__(self, transformer, r: int = 64, lora_alpha: float = 128.0, seed: int = 0, gradient_checkpointing: bool = True):
+    def __init__(self, transformer, r: int = 64, lora_alpha: float = 128.0, seed: int = 0, gradient_checkpointing=True):
+        """gradient_checkpointing: True = every block is recomputed in the backward (the reference's
+        `enable_gradient_checkpointing()`, 33 GiB at the 5B shapes); "mlp" = only the MLP half is recomputed and the
+        attention half keeps its activations (sized for the 180 GB of a B200: ~125 GiB, no second attention forward);
+        False = nothing is recomputed."""
+        if gradient_checkpointing not in (True, False, "mlp"):
+            raise RuntimeError('gradient_checkpointing must be True, False or "mlp"')
         if r % 64 != 0:
             raise RuntimeError("the LoRA rank must be a multiple of 64 (it is the N / K dimension of the LoRA GEMMs)")
         self.base = transformer
@@ -262,18 +268,17 @@ class LoRATrainableTransformer:
             w = self._wt[i] = (_t(blk.w_qkv), _t(blk.w_o), _t(blk.w_ff1), _t(blk.w_ff2))
         return w
 
-    # ------------------------------------------------------------------ one block
-    def _block(self, x, i, emb, seg, heads):
+    # ------------------------------------------------------------------ one block, as its attention and MLP halves
+    def _attn_half(self, x, i, emb, seg, heads):
         blk = self.base.blocks[i]
         c = self.config
         D = c.inner_dim
         B = emb.shape[0]
         S = seg[0]
-        wqkv_t, wo_t, wff1_t, wff2_t = self._wT(i)
+        wqkv_t, wo_t, _, _ = self._wT(i)
         lay = self.lora[i]
         with torch.no_grad():
             m = dense.linear_smallm(emb, blk.n1_lw, blk.n1_lb, act_in=dense.ACT_SILU)
-            m2 = dense.linear_smallm(emb, blk.n2_lw, blk.n2_lb, act_in=dense.ACT_SILU)
         n1 = _LNMod.apply(x, blk.n1_w, blk.n1_b, c.norm_eps, seg, m[:, 3 * D:4 * D], m[:, 4 * D:5 * D], m[:, 0:D], m[:, D:2 * D], 6 * D)
         ab = []
         for mod in ("to_q", "to_k", "to_v"):
@@ -282,12 +287,23 @@ class LoRATrainableTransformer:
         qkv = _HeadLN.apply(qkv, heads, blk.lnq, blk.lnk, 1e-6)
         att = _Attention.apply(qkv.view(B, S, 3 * D), heads).view(B * S, D)
         o = _LoRALinear.apply(att, blk.w_o, blk.b_o, wo_t, self.scaling, ((0, D),), lay["to_out.0"][0].to(BF16), lay["to_out.0"][1].to(BF16))
-        x = _GateRes.apply(x, o, seg, m[:, 5 * D:6 * D], m[:, 2 * D:3 * D], 6 * D)
+        return _GateRes.apply(x, o, seg, m[:, 5 * D:6 * D], m[:, 2 * D:3 * D], 6 * D)
+
+    def _mlp_half(self, x, i, emb, seg):
+        blk = self.base.blocks[i]
+        c = self.config
+        D = c.inner_dim
+        _, _, wff1_t, wff2_t = self._wT(i)
+        with torch.no_grad():
+            m2 = dense.linear_smallm(emb, blk.n2_lw, blk.n2_lb, act_in=dense.ACT_SILU)
         n2 = _LNMod.apply(x, blk.n2_w, blk.n2_b, c.norm_eps, seg, m2[:, 3 * D:4 * D], m2[:, 4 * D:5 * D], m2[:, 0:D], m2[:, D:2 * D], 6 * D)
         pre = _LoRALinear.apply(n2, blk.w_ff1, blk.b_ff1, wff1_t, self.scaling, ())
         act = _Gelu.apply(pre)
         f = _LoRALinear.apply(act, blk.w_ff2, blk.b_ff2, wff2_t, self.scaling, ())
         return _GateRes.apply(x, f, seg, m2[:, 5 * D:6 * D], m2[:, 2 * D:3 * D], 6 * D)
+
+    def _block(self, x, i, emb, seg, heads):
+        return self._mlp_half(self._attn_half(x, i, emb, seg, heads), i, emb, seg)
 
     # ------------------------------------------------------------------ forward
     def forward(self, hidden_states, encoder_hidden_states, timestep, num_layers: int | None = None):
@@ -324,8 +340,12 @@ class LoRATrainableTransformer:
         seg = (S, St)
         x = x0.view(B * S, D)
         L = c.num_layers if num_layers is None else num_layers
+        mode = self.gradient_checkpointing if torch.is_grad_enabled() else False
         for i in range(L):
-            if self.gradient_checkpointing and torch.is_grad_enabled():
+            if mode == "mlp":        # keep the attention half's activations (2.2 GB per block at the 5B shapes), recompute the MLP half
+                x = self._attn_half(x, i, emb, seg, heads)
+                x = checkpoint(self._mlp_half, x, i, emb, seg, use_reentrant=False)
+            elif mode:
                 x = checkpoint(self._block, x, i, emb, seg, heads, use_reentrant=False)
             else:
                 x = self._block(x, i, emb, seg, heads)
