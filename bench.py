@@ -394,7 +394,10 @@ def run_ours(args, rank, world, local):
         try:
             from videogpa_b200.train_dit import LoRATrainableTransformer
             from videogpa_b200.train_step import DPOSharedStep
-            pol = LoRATrainableTransformer(model, r=64, lora_alpha=128.0, gradient_checkpointing="mlp")
+            torch.cuda.empty_cache()
+            free_gib = torch.cuda.mem_get_info()[0] / 2 ** 30
+            ck_mode = "mlp" if free_gib > 135 else True           # the attention-activation plan needs ~110 GiB on top of the model
+            pol = LoRATrainableTransformer(model, r=64, lora_alpha=128.0, gradient_checkpointing=ck_mode)
             dstep = DPOSharedStep(model, None, beta=1.0, trainable=pol)
             opt = dstep.configure_optimizers()
             gt = torch.Generator().manual_seed(0)
@@ -414,7 +417,8 @@ def run_ours(args, rank, world, local):
                      "pairs_per_s": 1000.0 / tms, "forward_ms": ev[0].elapsed_time(ev[1]), "backward_ms": ev[1].elapsed_time(ev[2]),
                      "loss": float(tl.detach()), "lora_params": sum(p.numel() for p in pol.parameters()),
                      "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30, "weights": "random-init base, PEFT-initialised LoRA",
-                     "checkpointing": "MLP half recomputed, attention half kept (sized for 180 GB HBM; full-block recompute: 33 GiB, +0.6 s)"}
+                     "checkpointing": ("MLP half recomputed, attention half kept (sized for 180 GB HBM; full-block recompute: 33 GiB, +0.6 s)"
+                                       if ck_mode == "mlp" else "full-block recompute (not enough free HBM for the attention-activation plan)")}
             del pol, dstep, opt, tl
             torch.cuda.empty_cache()
         except Exception as ex:
