@@ -241,18 +241,23 @@ def test_dpo_training_step_gradients_vs_oracle_autograd(lib):
     assert names[0] == "base_model.model.transformer_blocks.0.attn1.to_q.lora_A.weight" and len(names) == 16
 
 
-def test_training_forward_matches_inference_with_zero_lora(lib):
+@pytest.mark.parametrize("variant", ["t2v", "i2v_posemb"])
+def test_training_forward_matches_inference_with_zero_lora(lib, variant):
     """With B = 0 (PEFT's initial state) the differentiable forward equals the inference transformer called without rotary
     embeddings up to the different rounding points of the unfused training path (<= 2e-2 of the max)."""
     from oracle import dit_torch as O
     from videogpa_b200.train_dit import LoRATrainableTransformer
     from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
     kw = dict(num_attention_heads=4, num_layers=2, text_embed_dim=256, sample_width=24, sample_height=16, sample_frames=9, max_text_seq_length=18)
+    cin = 16
+    if variant == "i2v_posemb":                               # train/CogVideoX-I2V-5B: in_channels 32, learned positional embedding
+        kw.update(in_channels=32, use_learned_positional_embeddings=True)
+        cin = 32
     sd = {k: v.to(BF).float() for k, v in O.random_state_dict(O.DiTConfig(**kw), seed=8, randomize_norms=True, std=0.05).items()}
     base = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
     pol = LoRATrainableTransformer(base)
     g = torch.Generator().manual_seed(4)
-    x = torch.randn(4, 3, 16, 16, 24, generator=g).cuda()
+    x = torch.randn(4, 3, cin, 16, 24, generator=g).cuda()
     e = torch.randn(4, 18, 256, generator=g).to(BF).cuda()
     t = torch.tensor([5, 300, 700, 999]).cuda()
     with torch.no_grad():

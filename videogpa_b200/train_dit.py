@@ -311,8 +311,8 @@ class LoRATrainableTransformer:
         autograd graph reaching the LoRA factors. No rotary embedding, as in the reference's training call."""
         t = self.base
         c = self.config
-        if (c.patch_size_t or 1) != 1 or t.pos_embedding is not None:
-            raise RuntimeError("the training forward covers the CogVideoX-5B T2V layout (no temporal patching, no learned pos-emb)")
+        if (c.patch_size_t or 1) != 1:
+            raise RuntimeError("the training forward covers the CogVideoX-5B T2V / I2V layouts (no temporal patching)")
         B, Fr, Cc, H, W = hidden_states.shape
         p, D, heads = c.patch_size, c.inner_dim, c.num_attention_heads
         dev = self.device
@@ -333,9 +333,15 @@ class LoRATrainableTransformer:
             emb = dense.linear_smallm(e1, t.t2_w, t.t2_b, act_in=dense.ACT_SILU)
             x0 = torch.empty((B, S, D), dtype=BF16, device=dev)
             patches = dense.patchify(hs.view(B * Fr, Cc, H, W))
+            epi = dense.EPI_BIAS
+            if t.pos_embedding is not None:                        # CogVideoX-5B-I2V: learned positional embedding (frozen)
+                if t.pos_embedding.shape[1] < S:
+                    raise RuntimeError("pos_embedding is shorter than the token sequence")
+                x0.copy_(t.pos_embedding[:, :S].expand(B, S, D))
+                epi = dense.EPI_GATE_RES
             for b in range(B):
-                dense.linear(enc_in[b], t.text_w, t.text_b, out=x0[b, :St])
-                dense.linear(patches[b * Sv:(b + 1) * Sv], t.patch_w, t.patch_b, out=x0[b, St:])
+                dense.linear(enc_in[b], t.text_w, t.text_b, out=x0[b, :St], epilogue=epi)
+                dense.linear(patches[b * Sv:(b + 1) * Sv], t.patch_w, t.patch_b, out=x0[b, St:], epilogue=epi)
             mo = dense.linear_smallm(emb, t.no_lw, t.no_lb, act_in=dense.ACT_SILU)
         seg = (S, St)
         x = x0.view(B * S, D)
