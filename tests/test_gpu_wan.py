@@ -133,3 +133,28 @@ def test_wan_lora_merge_vs_oracle(lib, tmp_path):
         got = model.attention_weight(layer, mod).cpu()
         diff = (got.float() - ref.float()).abs()
         assert (got != ref).float().mean() < 0.01 and diff.max() <= 2.0 ** -7 * ref.float().abs().max()
+
+
+def test_wan_generate_cli_synthetic(lib, tmp_path, capsys):
+    """generate/Wan2.2-TI2V-5B.py surface on the GPU with a 1-block random DiT: image resolution through --base_dir, missing
+    image skipped, skip-if-exists on the second run, final latent with the first frame clamped to the image latent."""
+    import json
+    from videogpa_b200.generate import wan2_2_ti2v_5b as g
+    (tmp_path / "imgs").mkdir()
+    (tmp_path / "imgs" / "a.png").write_bytes(b"bytes that seed the synthetic first-frame latent")
+    pj = tmp_path / "p.json"
+    pj.write_text(json.dumps({"s1": {"text_prompt": "a boat", "image_prompt": "a.png"}, "s2": {"text_prompt": "a car", "image_prompt": "missing.png"},
+                              "s3": {"text_prompt": "no image"}}))
+    out = tmp_path / "out"
+    argv = ["--model_path", "unused", "--prompt_json", str(pj), "--output_dir", str(out), "--base_dir", str(tmp_path / "imgs"),
+            "--synthetic", "1", "--sampling_steps", "3", "--frame_num", "9", "--height", "128", "--width", "192"]
+    g.main(argv)
+    txt = capsys.readouterr().out
+    assert "Failed" not in txt and "Image not found" in txt, txt
+    lat = torch.load(str(out / "s1" / "seed_42.latents.pt"))
+    assert lat.shape == (48, 3, 8, 12) and lat.dtype == torch.bfloat16 and torch.isfinite(lat.float()).all()
+    first = g._seeded(str(tmp_path / "imgs" / "a.png"), (48, 1, 8, 12), "img").to(torch.bfloat16)
+    assert torch.equal(lat[:, :1], first)                       # TI2V: the image frame is kept
+    assert not (out / "s2").exists() and not (out / "s3").exists()
+    g.main(argv)
+    assert "Skip existing: s1" in capsys.readouterr().out

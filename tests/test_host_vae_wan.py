@@ -137,3 +137,25 @@ def test_t5_abi_argument_validation():
     assert L.vgpa_t5_attention_bf16(16, 16, 16, 16, 16, 1, 2, 8, 64, 128, None) != 0
     assert L.vgpa_gated_mul_bf16(16, 16, 16, 4, 12, 16, 16, 16, None) != 0 and b"multiple of 8" in L.vgpa_last_error()
     assert L.vgpa_gated_mul_bf16(16, 16, 16, 4, 16, 8, 16, 16, None) != 0
+
+
+def test_wan_generate_cli_surface(tmp_path):
+    """generate/Wan2.2-TI2V-5B.py:140-153 flags and defaults, task parsing (:77-89) and the latent grid of the Wan2.2 VAE
+    strides (81 frames 704x1280 -> 21 x 44 x 80 latents -> 18 480 tokens, BASELINE.json configs[3])."""
+    import json
+    from videogpa_b200.generate import wan2_2_ti2v_5b as g
+    p = g.build_parser()
+    a = p.parse_args(["--model_path", "m", "--prompt_json", "p.json", "--output_dir", "o"])
+    assert (a.lora_path, a.lora_weight, a.base_dir, a.gpu_id, a.seed, a.num_prompts, a.frame_num, a.shift, a.sampling_steps,
+            a.guide_scale, a.fps) == (None, 0.2, None, 0, 42, None, 81, 5.0, 50, 5.0, 24)
+    with pytest.raises(SystemExit):
+        p.parse_args(["--prompt_json", "p.json", "--output_dir", "o"])          # --model_path is required
+    assert g.latent_grid(81, 704, 1280) == (21, 44, 80, 18480)
+    f = tmp_path / "p.json"
+    f.write_text(json.dumps({"a/b": {"text_prompt": "x", "image_prompt": "i.png"}, "c": {"prompt": "y", "image_path": "j.png"}}))
+    t = g.load_tasks(str(f), None)
+    assert [k for k, _ in t] == ["a/b", "c"] and g.load_tasks(str(f), 1) == t[:1]
+    f.write_text(json.dumps([{"group_id": 7, "text_prompt": "x"}, {"text_prompt": "y"}]))
+    assert [k for k, _ in g.load_tasks(str(f), None)] == [7, 1]
+    f.write_text(json.dumps("nope"))
+    assert g.load_tasks(str(f), None) is None
