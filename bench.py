@@ -280,6 +280,8 @@ def run_ours(args, rank, world, local):
     # ---- secondary metric of BASELINE.json: MVCS scores/s at the DA3 production size, batched
     mvcs = None
     try:
+        if world > 1:
+            raise RuntimeError("reported at N = 1 only")
         N, T, H, W = 128, 10, 504, 504
         gd = torch.Generator(device=dev).manual_seed(0)
         depth = 2.0 + 0.5 * torch.rand(N, T, H, W, generator=gd, device=dev)
@@ -308,6 +310,8 @@ def run_ours(args, rank, world, local):
     # ---- VAE decode of the finished clip (part of the same path; reported separately)
     vae = None
     try:
+        if world > 1:
+            raise RuntimeError("reported at N = 1 only")
         from videogpa_b200.vae import AutoencoderKLCogVideoXDecoder, VAEDecoderConfig
         dec = AutoencoderKLCogVideoXDecoder.random_init(VAEDecoderConfig(), seed=5, device=dev)
         dec.enable_tiling(); dec.enable_slicing()
@@ -329,6 +333,8 @@ def run_ours(args, rank, world, local):
     # ---- the encoders either side of the path: VAE encode of a 49-frame clip, T5-XXL prompt encode
     enc_leg = None
     try:
+        if world > 1:
+            raise RuntimeError("reported at N = 1 only")
         from videogpa_b200.t5 import T5Config, T5EncoderModel
         from videogpa_b200.vae import AutoencoderKLCogVideoXEncoder
         ve = AutoencoderKLCogVideoXEncoder.random_init(VAEDecoderConfig(), seed=6, device=dev)
@@ -363,6 +369,8 @@ def run_ours(args, rank, world, local):
     # ---- Wan2.2-TI2V-5B guided denoise step (BASELINE.json configs[3] shapes: 81 frames 1280x704, S = 18 480), reported beside
     wan = None
     try:
+        if world > 1:
+            raise RuntimeError("reported at N = 1 only")
         from videogpa_b200.wan import WanConfig, WanDenoiseStep, WanTransformer3D, flow_sigmas
         wm = WanTransformer3D.random_init(WanConfig.ti2v_5b(), seed=21, device=dev)
         wstep = WanDenoiseStep(wm, guide_scale=5.0)
