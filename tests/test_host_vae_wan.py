@@ -159,3 +159,40 @@ def test_wan_generate_cli_surface(tmp_path):
     assert [k for k, _ in g.load_tasks(str(f), None)] == [7, 1]
     f.write_text(json.dumps("nope"))
     assert g.load_tasks(str(f), None) is None
+
+
+def test_flow_unipc_scheduler_orders_and_schedule():
+    """schedulers.FlowUniPCMultistepScheduler (WanTI2V.generate's default sampler) on a linear flow with the exact solution
+    x(s) = x(s0) (s / s0)^(1 - a): UniPC-p is of order p + 1, so halving the step divides the error by ~4 (p = 1) and ~8
+    (p = 2); the last step (sigma -> 0) returns the data prediction; the shifted schedule matches its closed form."""
+    import math
+    import numpy as np
+    from videogpa_b200.schedulers import FlowUniPCMultistepScheduler
+    a = 0.3
+
+    def err(N, order):
+        sch = FlowUniPCMultistepScheduler(solver_order=order, lower_order_final=False)
+        sch.set_timesteps(N, sigmas=np.exp(np.linspace(math.log(0.95), math.log(0.05), N + 1)))
+        x = torch.ones(2)
+        for i in range(N):
+            x = sch.step(x * (1 - a) / sch.sigmas[i], x)
+        return abs(float(x[0]) - (0.05 / 0.95) ** (1 - a))
+
+    e1 = [err(N, 1) for N in (8, 16, 32)]
+    e2 = [err(N, 2) for N in (8, 16, 32)]
+    assert 3.5 < e1[0] / e1[1] < 4.5 and 3.5 < e1[1] / e1[2] < 4.5
+    assert 6.0 < e2[0] / e2[1] < 10.0 and 6.0 < e2[1] / e2[2] < 10.0
+    assert e2[2] < e1[2] / 30
+    sch = FlowUniPCMultistepScheduler()
+    sch.set_timesteps(50, shift=5.0)
+    lin = np.linspace(0.999, 0.0, 51)[:-1]
+    assert np.allclose(sch.sigmas[:-1], 5.0 * lin / (1 + 4.0 * lin)) and sch.sigmas[-1] == 0.0 and len(sch.timesteps) == 50
+    assert abs(sch.timesteps[0] - 1000 * 5.0 * 0.999 / (1 + 4.0 * 0.999)) < 1e-9
+    x = torch.full((3,), 2.0)
+    for i in range(50):
+        x = sch.step(x * (1 - a) / sch.sigmas[i], x)          # perfect-model limit: the final sample is the last x0 prediction
+    assert torch.isfinite(x).all() and float(x[0]) > 0
+    with pytest.raises(RuntimeError):
+        FlowUniPCMultistepScheduler().step(torch.zeros(1), torch.zeros(1))
+    with pytest.raises(RuntimeError):
+        sch.set_timesteps(3, sigmas=[0.5, 0.6, 0.2, 0.1])

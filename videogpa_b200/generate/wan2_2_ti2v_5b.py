@@ -8,7 +8,8 @@ skipped, `Image not found ... skipping`, `<output_dir>/<group_id>/seed_<seed>.*`
 
 What runs here: the guided denoise loop of `WanTI2V.generate` on videogpa_b200 kernels — 30-block DiT with per-token
 timesteps (first latent frame t = 0 and clamped to the encoded image), cond / uncond forwards, `uncond + g (cond - uncond)`,
-shifted flow-matching schedule (`--shift`), Euler update (the reference's UniPC corrector is not built). The un-vendored Wan2.2
+shifted flow-matching schedule (`--shift`) and the UniPC multistep sampler that `WanTI2V.generate` defaults to
+(schedulers.FlowUniPCMultistepScheduler; `sample_solver="euler"` selects the fused Euler step). The un-vendored Wan2.2
 repository's umT5 text encoder and Wan-VAE are outside this build, so the result of a prompt is the final latent
 `seed_<seed>.latents.pt` ([48, F, h, w], bf16) instead of an mp4, and inputs are either synthetic (`--synthetic N`: N-block
 random DiT, context / first-frame latent seeded from the prompt and image bytes) or precomputed next to the image:
@@ -57,7 +58,8 @@ class WanTI2VEngine:
         self._step = WanDenoiseStep
 
     @torch.no_grad()
-    def generate(self, context, first_latent, frame_num=81, shift=5.0, sampling_steps=50, guide_scale=5.0, seed=42, size=(704, 1280)):
+    def generate(self, context, first_latent, frame_num=81, shift=5.0, sampling_steps=50, guide_scale=5.0, seed=42, size=(704, 1280),
+                 sample_solver="unipc"):
         from ..wan import flow_sigmas
         F_, h, w, S = latent_grid(frame_num, size[0], size[1])
         if tuple(first_latent.shape) != (self.model.config.in_dim, 1, h, w):
@@ -68,12 +70,26 @@ class WanTI2VEngine:
         lat[:, :1] = first
         hw = (h // 2) * (w // 2)
         step = self._step(self.model, guide_scale=guide_scale)
-        sig = flow_sigmas(sampling_steps, shift)
         null = torch.zeros(1, context.shape[-1], device=self.device, dtype=BF16)
         ctx = context.to(device=self.device, dtype=BF16)
+        if sample_solver == "unipc":                                   # WanTI2V.generate's default sampler
+            from ..schedulers import FlowUniPCMultistepScheduler
+            sch = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1.0)
+            sch.set_timesteps(sampling_steps, shift=shift)
+            x = lat.float()
+            for i in range(sampling_steps):
+                t = torch.full((1, S), float(sch.timesteps[i]))
+                t[:, :hw] = 0                                          # the image frame is clean: t = 0 for its tokens
+                v = step.guided_velocity(x, t, ctx, null)
+                x = sch.step(v, x)
+                x[:, :1] = first.float()                               # TI2V: the first latent frame stays the encoded image
+            return x.to(BF16)
+        if sample_solver != "euler":
+            raise RuntimeError(f"unknown sample_solver {sample_solver!r} (unipc | euler)")
+        sig = flow_sigmas(sampling_steps, shift)
         for i in range(sampling_steps):
             t = torch.full((1, S), sig[i] * 1000.0)
-            t[:, :hw] = 0                                              # the image frame is clean: t = 0 for its tokens
+            t[:, :hw] = 0
             lat = step(lat, t, sig[i], sig[i + 1], ctx, null, first_frame=first)
         return lat
 

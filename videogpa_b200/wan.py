@@ -325,10 +325,19 @@ class WanDenoiseStep:
     """One guided denoise step of the Wan sampler loop: cond and uncond forwards (separate, as in WanTI2V.generate),
     `uncond + g (cond - uncond)` and a flow-matching Euler update, fused in vgpa_cfg_scheduler_step. `cfg_group`
     (parallel.CfgPairGroup) shards the two branches over two ranks with one all-gather of the prediction per step.
-    The UniPC multistep corrector of the reference sampler is not built yet (next row)."""
+    `guided_velocity` + schedulers.FlowUniPCMultistepScheduler is the reference's default UniPC sampler (generate CLI)."""
 
     def __init__(self, model: WanTransformer3D, guide_scale: float = 5.0):
         self.model, self.guide_scale = model, guide_scale
+
+    @torch.no_grad()
+    def guided_velocity(self, latent, t_tokens, context, context_null) -> torch.Tensor:
+        """cond and uncond forwards + `uncond + g (cond - uncond)` in fp32 (WanTI2V.generate's noise_pred): the input of a
+        multistep sampler such as schedulers.FlowUniPCMultistepScheduler, which keeps the latent in fp32 between steps."""
+        lat = latent.to(device=self.model.device, dtype=BF16).contiguous()
+        cond = self.model([lat], t_tokens, [context])[0].float()
+        uncond = self.model([lat], t_tokens, [context_null])[0].float()
+        return uncond + self.guide_scale * (cond - uncond)
 
     @torch.no_grad()
     def __call__(self, latent, t_tokens, sigma: float, sigma_next: float, context, context_null, cfg_group=None, first_frame=None):
