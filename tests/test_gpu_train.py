@@ -264,3 +264,31 @@ def test_training_forward_matches_inference_with_zero_lora(lib, variant):
         a = pol(x, e, t)
         b = base(x, encoder_hidden_states=e, timestep=t).sample
     assert a.shape == b.shape and relmax(a, b) < 2e-2
+
+
+def test_lora_save_pretrained_round_trip(lib, tmp_path):
+    """Train-side `save_pretrained` -> generate-side `--lora_path` merge: the adapter directory written by the trainable wrapper
+    is read back by lora.merge_lora and yields W + (alpha / r) B A on the merged transformer (reference 03_train.py:287 ->
+    generate/CogVideoX-5B.py:24-31)."""
+    from oracle import dit_torch as O
+    from videogpa_b200.lora import merge_lora, read_adapter
+    from videogpa_b200.train_dit import TARGETS, LoRATrainableTransformer
+    from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+    kw = dict(num_attention_heads=4, num_layers=2, text_embed_dim=256, sample_width=24, sample_height=16, sample_frames=9, max_text_seq_length=18)
+    sd = {k: v.to(BF).float() for k, v in O.random_state_dict(O.DiTConfig(**kw), seed=9, std=0.05).items()}
+    base = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
+    pol = LoRATrainableTransformer(base, r=64, lora_alpha=128.0, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    with torch.no_grad():
+        for layer in pol.lora:
+            for m in TARGETS:
+                layer[m][1].copy_(0.05 * torch.randn(layer[m][1].shape, device="cuda", generator=g))
+    out = tmp_path / "final_lora"
+    pol.save_pretrained(str(out))
+    cfg, pairs = read_adapter(str(out))
+    assert cfg["r"] == 64 and cfg["lora_alpha"] == 128.0 and sorted(cfg["target_modules"]) == sorted(TARGETS) and len(pairs) == 8
+    fresh = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
+    w0 = fresh.attention_weight(1, "to_k").float().clone()
+    assert merge_lora(fresh, str(out)) == 8
+    want = w0 + pol.merged_delta(1, "to_k")
+    assert relmax(fresh.attention_weight(1, "to_k"), want) < 1e-2

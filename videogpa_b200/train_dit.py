@@ -256,6 +256,21 @@ class LoRATrainableTransformer:
         """The tensors PEFT's save_pretrained writes to adapter_model.safetensors (reference 03_train.py:287)."""
         return {k: v.detach().clone() for k, v in self.named_parameters()}
 
+    def save_pretrained(self, path: str) -> None:
+        """`model.transformer.save_pretrained(out / "final_lora")` (reference 03_train.py:287): a PEFT adapter directory —
+        adapter_config.json + adapter_model.safetensors with PEFT's saved key form (`...lora_A.weight`, no adapter name) —
+        that `--lora_path` of the generate CLIs (lora.merge_lora) and PEFT itself can load."""
+        import json
+        import os
+        from safetensors.torch import save_file
+        os.makedirs(path, exist_ok=True)
+        cfg = {"peft_type": "LORA", "task_type": None, "base_model_name_or_path": None, "r": self.r, "lora_alpha": self.lora_alpha,
+               "lora_dropout": 0.0, "target_modules": list(TARGETS), "bias": "none", "fan_in_fan_out": False, "use_dora": False,
+               "use_rslora": False, "inference_mode": True, "init_lora_weights": True, "modules_to_save": None}
+        with open(os.path.join(path, "adapter_config.json"), "w", encoding="utf-8") as f:
+            json.dump(cfg, f, indent=2)
+        save_file({k: v.detach().to("cpu").contiguous() for k, v in self.named_parameters()}, os.path.join(path, "adapter_model.safetensors"))
+
     def merged_delta(self, layer: int, module: str) -> torch.Tensor:
         A, Bm = self.lora[layer][module]
         return (self.scaling * (Bm @ A)).detach()
