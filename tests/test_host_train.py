@@ -68,3 +68,26 @@ def test_dpo_step_requires_trainable_for_training():
     step = DPOSharedStep(_T(), _T())
     with pytest.raises(RuntimeError):
         step.training_step({})
+
+
+def test_train_cli_config_and_schedule(tmp_path):
+    """train/CogVideoX-5B/03_train.py: DEFAULT_CONFIG values (:39-81), YAML `training:` override and --devices parsing
+    (:290-305), the cosine-with-warm-up multiplier of diffusers' get_cosine_schedule_with_warmup, the 98/2 split (:237-242)."""
+    import math
+    from videogpa_b200.train import cogvideox_5b as t
+    c = t.DEFAULT_CONFIG
+    assert (c["learning_rate"], c["beta"], c["max_steps"], c["warmup_steps"], c["batch_size"], c["accumulate_grad_batches"],
+            c["gradient_clip_val"], c["lora_rank"], c["lora_alpha"], c["min_gap"], c["metric_mode"]) == \
+        (5e-6, 1.0, 10000, 500, 1, 2, 1.0, 64, 128.0, 0.05, "min")
+    y = tmp_path / "cfg.yaml"
+    y.write_text("training:\n  max_steps: 7\n  learning_rate: 1.0e-4\nother:\n  x: 1\n")
+    cfg = t.load_config(t.build_parser().parse_args(["--config", str(y), "--devices", "2,3", "--base_path", "/data"]))
+    assert cfg["max_steps"] == 7 and cfg["learning_rate"] == 1e-4 and cfg["devices"] == [2, 3] and cfg["base_path"] == "/data"
+    assert cfg["warmup_steps"] == 500                                  # untouched keys keep the defaults
+    f = t.cosine_schedule_with_warmup
+    assert f(0, 500, 10000) == 0.0 and f(250, 500, 10000) == 0.5 and f(500, 500, 10000) == 1.0
+    assert abs(f(5250, 500, 10000) - 0.5) < 1e-12 and abs(f(10000, 500, 10000)) < 1e-12
+    assert abs(f(2875, 500, 10000) - 0.5 * (1 + math.cos(math.pi * 0.25))) < 1e-12
+    tr, va = t.split_dataset(list(range(100)))
+    tr2, _ = t.split_dataset(list(range(100)))
+    assert len(tr) == 98 and len(va) == 2 and list(tr.indices) == list(tr2.indices)

@@ -37,6 +37,18 @@ def _t(x: torch.Tensor) -> torch.Tensor:
     return x.t().contiguous()
 
 
+def _t_rows(x: torch.Tensor) -> torch.Tensor:
+    """[M, C] -> [C, M'] with the token dimension zero-padded to a multiple of 8: it becomes the K dimension of a weight-
+    gradient GEMM (K % 8 == 0 for the 16-byte TMA row pitch); zero columns on both operands leave the product unchanged."""
+    M = x.shape[0]
+    Mp = (M + 7) // 8 * 8
+    if Mp == M:
+        return x.t().contiguous()
+    out = x.new_zeros((x.shape[1], Mp))
+    out[:, :M] = x.t()
+    return out
+
+
 def _ln_args(x, w, eps, seg, scale_txt, scale_vid, mod_stride_b):
     a = LayerNormArgs()
     a.x, a.rows, a.D, a.ldx = x.data_ptr(), x.shape[0], x.shape[1], x.stride(0)
@@ -97,14 +109,14 @@ class _LoRALinear(torch.autograd.Function):
         need_da = ctx.needs_input_grad[0]                                     # false for block 0 (its input has no graph)
         da = dense.linear(dy, wt) if need_da else None                        # dgrad through the frozen weight
         grads = []
-        a_t = _t(a) if n_ad else None                                         # [K, M], shared by the adapters of this input
+        a_t = _t_rows(a) if n_ad else None                                    # [K, M], shared by the adapters of this input
         for i, (c0, n) in enumerate(cols):
             A, Bm, u = ab[2 * i], ab[2 * i + 1], us[i]
             dyi = dy[:, c0:c0 + n]
             du = dense.linear(dyi, _t((Bm.float() * s).to(BF16)))             # [M, r] = dy_i (s B)
-            dB = dense.linear(_t(dyi), _t(u))                                 # [n, r] = dy_i^T u
+            dB = dense.linear(_t_rows(dyi), _t_rows(u))                       # [n, r] = dy_i^T u
             dB = (dB.float() * s).to(BF16)
-            dA = dense.linear(_t(du), a_t)                                    # [r, K] = du^T a
+            dA = dense.linear(_t_rows(du), a_t)                               # [r, K] = du^T a
             if need_da:
                 dense.linear(du, _t(A), out=da, epilogue=dense.EPI_GATE_RES)  # da += du A
             grads += [dA, dB]
@@ -338,8 +350,6 @@ class LoRATrainableTransformer:
             hw = (H // p) * (W // p)
             Sv = Fr * hw
             S = St + Sv
-            if (B * S) % 8 != 0:
-                raise RuntimeError("the LoRA weight-gradient GEMMs need B * (text + video tokens) to be a multiple of 8")
             ts = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32)
             if ts.numel() == 1 and B > 1:
                 ts = ts.expand(B).contiguous()

@@ -53,8 +53,12 @@ class DPOSharedStep:
     @torch.no_grad()
     def _shared_step(self, batch: dict, generator=None, timesteps=None, noise=None) -> LossOutput:
         B, pair, emb2, t2, v_win_target, v_lose_target = self._prepare(batch, generator, timesteps, noise)
-        v_pred = self.transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
-        v_ref = self.ref_transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
+        if self.trainable is not None:                  # the policy being trained (base + unmerged LoRA), without a graph
+            v_pred = self.trainable(pair, emb2, t2)
+        else:
+            v_pred = self.transformer(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
+        ref = self.ref_transformer if self.ref_transformer is not None else self.trainable.base
+        v_ref = ref(pair, encoder_hidden_states=emb2, timestep=t2, return_dict=True).sample
         return self.loss_fn(v_pred[:B].contiguous(), v_pred[B:].contiguous(), v_ref[:B].contiguous(), v_ref[B:].contiguous(),
                             v_win_target, v_lose_target)
 
