@@ -42,5 +42,27 @@ epipolar_from_matches(p1, p1 + torch.rand(2, 64, 2, device="cuda", generator=g),
 ts = [torch.randn(2, 3, 4, 8, 8, device="cuda", generator=g) for _ in range(6)]
 ts[0].requires_grad_(True); ts[1].requires_grad_(True)
 DPOLoss(beta=2.0)(*ts).loss.backward()
+# round-1 additions: VAE encoder (plain GroupNorm path, strided conv via subsampling), T5 encoder (bias attention, gated product),
+# training step (attention backward, row-wise backward kernels, LoRA dgrad / wgrad GEMMs) with an odd token count
+from videogpa_b200.vae import AutoencoderKLCogVideoXEncoder
+from videogpa_b200.t5 import T5Config, T5EncoderModel
+from videogpa_b200.train_dit import LoRATrainableTransformer
+from videogpa_b200.train_step import DPOSharedStep
+enc = AutoencoderKLCogVideoXEncoder.random_init(VAEDecoderConfig(block_out_channels=(64, 64, 64, 128), sample_height=96, sample_width=160), seed=4, device="cuda")
+enc.enable_tiling()
+enc.encode((torch.rand(1, 3, 9, 96, 160, device="cuda", generator=g) * 2 - 1).to(BF))
+t5 = T5EncoderModel.random_init(T5Config(vocab_size=64, d_model=256, d_ff=512, num_layers=1, num_heads=4), seed=5, device="cuda")
+t5.use_cuda_graph = False
+t5(torch.randint(0, 64, (2, 37), device="cuda", generator=g))
+pol = LoRATrainableTransformer(m, r=64, lora_alpha=128.0, gradient_checkpointing="mlp")
+with torch.no_grad():
+    for layer in pol.lora:
+        for k in layer:
+            layer[k][1].normal_(0, 0.02)
+step = DPOSharedStep(m, None, beta=5.0, trainable=pol)
+gc = torch.Generator().manual_seed(1)
+batch = {"x_win": torch.randn(1, 16, 3, 16, 24, generator=gc), "x_lose": torch.randn(1, 16, 3, 16, 24, generator=gc),
+         "prompt_emb": torch.randn(1, 18, 256, generator=gc).to(BF)}          # 2 x 306 tokens: not a multiple of 8, partial tiles everywhere
+step.training_step(batch).backward()
 torch.cuda.synchronize()
 print("sanitize run complete")
