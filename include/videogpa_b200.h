@@ -167,6 +167,9 @@ int vgpa_head_layernorm_bf16(const void* x, const void* dy, void* out, int64_t r
                              int64_t ldo, const float* weight, const float* bias, float eps, int backward, void* stream);
 /* GELU(tanh) on n contiguous bf16 values. backward = 0: out = gelu(x). backward = 1: out = dy * gelu'(x). */
 int vgpa_gelu_tanh_bf16(const void* x, const void* dy, void* out, int64_t n, int backward, void* stream);
+/* out[c, r] = x[r, c] for r < rows and 0 for rows <= r < ldo: the [tokens, features] -> [features, tokens (padded to the
+ * GEMM's K granularity)] operand of the LoRA weight-gradient GEMMs dB = dy^T u, dA = du^T a. ldx, ldo even. */
+int vgpa_transpose_bf16(const void* x, void* out, int rows, int cols, int64_t ldx, int64_t ldo, void* stream);
 /* out[r, :] = [add[r, :] +] x[r, :] * gate[b(r), seg(r)][:]: the adaLN-zero gated residual `hidden + gate * branch` (bf16
  * product, then bf16 sum) out of place for the training path, and its backward (add = NULL). */
 int vgpa_scale_cols_bf16(const void* x, const void* add, void* out, int rows, int D, int64_t ldx, int64_t ld_add, int64_t ldo,

@@ -327,3 +327,15 @@ def test_train_cli_synthetic_end_to_end(lib, tmp_path, capsys):
     assert acfg["r"] == 64 and len(pairs) == 4                      # one block x to_q / to_k / to_v / to_out.0
     A, Bm = pairs[(0, "to_q")]
     assert float(Bm.abs().max()) > 0                                # B left its zero initialisation
+
+
+@pytest.mark.parametrize("M,C_,ld", [(306, 256, 256), (612, 64, 768), (37, 130, 130), (128, 64, 64)])
+def test_transpose_kernel_bit_exact(lib, M, C_, ld):
+    """vgpa_transpose_bf16 (operands of the LoRA weight-gradient GEMMs): exact copy, strided input, zero-padded token columns."""
+    from videogpa_b200.train_dit import _t_rows
+    g = torch.Generator().manual_seed(M)
+    buf = torch.randn(M, ld, generator=g).to(BF).cuda()
+    x = buf[:, :C_]
+    out = _t_rows(x)
+    Mp = (M + 7) // 8 * 8
+    assert out.shape == (C_, Mp) and torch.equal(out[:, :M], x.t()) and (Mp == M or float(out[:, M:].abs().max()) == 0.0)

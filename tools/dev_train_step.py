@@ -17,7 +17,7 @@ opt = step.configure_optimizers()
 g = torch.Generator().manual_seed(0)
 batch = {"x_win": torch.randn(1, 16, 13, 60, 90, generator=g), "x_lose": torch.randn(1, 16, 13, 60, 90, generator=g),
          "prompt_emb": torch.randn(1, 226, 4096, generator=g).to(torch.bfloat16)}
-for it in range(3):
+for it in range(int(os.environ.get("ITERS", "3"))):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record()

@@ -140,6 +140,7 @@ SIGNATURES = {
     "vgpa_layernorm_modulate_bwd_bf16": (c_int, [C.POINTER(LayerNormArgs), c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
     "vgpa_head_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_float, c_int, c_void_p]),
     "vgpa_gelu_tanh_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "vgpa_transpose_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_void_p]),
     "vgpa_scale_cols_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_int, c_int, c_void_p, c_void_p, c_i64, c_void_p]),
     "vgpa_layernorm_modulate_bf16": (c_int, [C.POINTER(LayerNormArgs), c_void_p]),
     "vgpa_linear_smallm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_i64, c_int, c_void_p]),

@@ -240,6 +240,33 @@ scale_cols_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------- bf16 transpose
+// out[c, r] = x[r, c] for r < rows, 0 for rows <= r < ldo (the padded token columns of a weight-gradient GEMM operand).
+// 64 x 64 tiles through shared memory, 4-byte accesses on both sides.
+constexpr int TP = 64;
+__global__ void __launch_bounds__(256)
+transpose_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int cols, long long ldx, long long ldo) {
+  __shared__ __nv_bfloat16 tile[TP][TP + 2];
+  const int r0 = blockIdx.y * TP, c0 = blockIdx.x * TP;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;          // 8 warps
+  for (int i = w; i < TP; i += 8) {                                   // row r0 + i: lanes read column pairs
+    const int r = r0 + i, c = c0 + 2 * lane;
+    uint32_t v = 0;
+    if (r < rows && c + 1 < cols) v = *reinterpret_cast<const uint32_t*>(x + r * ldx + c);
+    else if (r < rows && c < cols) v = *reinterpret_cast<const unsigned short*>(x + r * ldx + c);
+    *reinterpret_cast<uint32_t*>(&tile[i][2 * lane]) = v;
+  }
+  __syncthreads();
+  for (int i = w; i < TP; i += 8) {                                   // output row c0 + i: lanes write row pairs r0 + 2 lane
+    const int c = c0 + i, r = r0 + 2 * lane;
+    if (c >= cols || r >= ldo) continue;
+    const unsigned short lo = *reinterpret_cast<const unsigned short*>(&tile[2 * lane][i]);
+    const unsigned short hi = *reinterpret_cast<const unsigned short*>(&tile[2 * lane + 1][i]);
+    if (r + 1 < ldo) *reinterpret_cast<uint32_t*>(out + c * ldo + r) = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+    else *reinterpret_cast<unsigned short*>(out + c * ldo + r) = lo;
+  }
+}
+
 inline unsigned grid_1d(long long n, int block) {
   long long g = (n + block - 1) / block;
   const long long cap = 148ll * 16;
@@ -340,5 +367,20 @@ extern "C" int vgpa_scale_cols_bf16(const void* x, const void* add, void* out, i
       ld_add, ldo, rows_per_sample, text_rows,
       static_cast<const __nv_bfloat16*>(gate_txt), static_cast<const __nv_bfloat16*>(gate_vid), gate_stride_b);
   VGPA_LAUNCH_CHECK("scale_cols_kernel");
+  return 0;
+}
+
+extern "C" int vgpa_transpose_bf16(const void* x, void* out, int rows, int cols, int64_t ldx, int64_t ldo, void* stream) {
+  using namespace vgpa;
+  VGPA_CHECK(x && out, "vgpa_transpose_bf16: null pointer");
+  VGPA_CHECK(rows > 0 && cols > 0 && ldx >= cols && ldo >= rows, "vgpa_transpose_bf16: bad shape rows=%d cols=%d ldx=%lld ldo=%lld", rows, cols,
+             (long long)ldx, (long long)ldo);
+  VGPA_CHECK(ldx % 2 == 0 && ldo % 2 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 3) == 0,
+             "vgpa_transpose_bf16: leading dimensions must be even and pointers 4-byte aligned");
+  const dim3 grid(static_cast<unsigned>((cols + TP - 1) / TP), static_cast<unsigned>((ldo + TP - 1) / TP));
+  VGPA_CHECK(grid.y < 65536, "vgpa_transpose_bf16: too many rows");
+  transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out),
+                                                                          rows, cols, ldx, ldo);
+  VGPA_LAUNCH_CHECK("transpose_kernel");
   return 0;
 }

@@ -40,12 +40,12 @@ def _t(x: torch.Tensor) -> torch.Tensor:
 def _t_rows(x: torch.Tensor) -> torch.Tensor:
     """[M, C] -> [C, M'] with the token dimension zero-padded to a multiple of 8: it becomes the K dimension of a weight-
     gradient GEMM (K % 8 == 0 for the 16-byte TMA row pitch); zero columns on both operands leave the product unchanged."""
-    M = x.shape[0]
+    M, Cc = x.shape
     Mp = (M + 7) // 8 * 8
-    if Mp == M:
-        return x.t().contiguous()
-    out = x.new_zeros((x.shape[1], Mp))
-    out[:, :M] = x.t()
+    if x.stride(1) != 1 or x.stride(0) % 2 or x.data_ptr() % 4:
+        x = x.contiguous()
+    out = torch.empty((Cc, Mp), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().vgpa_transpose_bf16(x.data_ptr(), out.data_ptr(), M, Cc, x.stride(0), Mp, _lib.current_stream()), "vgpa_transpose_bf16")
     return out
 
 
