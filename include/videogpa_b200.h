@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VGPA_ABI_VERSION 1
+#define VGPA_ABI_VERSION 2 /* 2: vgpa_attention_args gained `lse`; backward / training, T5 and transpose entry points added */
 
 /* ------------------------------------------------------------------------------------------------
  * runtime

@@ -32,7 +32,7 @@ def test_binding_table_matches_header():
 
 
 def test_loads_without_gpu_and_reports_errors(lib):
-    assert lib.vgpa_abi_version() == 1
+    assert lib.vgpa_abi_version() == 2
     # argument validation happens before any CUDA call, so it is checkable on a CPU-only host
     rc = lib.vgpa_linear_bf16(None, None)
     assert rc != 0 and b"null args" in lib.vgpa_last_error()

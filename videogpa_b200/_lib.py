@@ -184,6 +184,9 @@ def lib_path() -> Path:
     return _LIB_PATH
 
 
+ABI_VERSION = 2          # VGPA_ABI_VERSION of include/videogpa_b200.h
+
+
 def load():
     """Load the library once; raise loudly if it has not been built."""
     global _lib
@@ -198,6 +201,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.vgpa_abi_version() != ABI_VERSION:           # a stale in-tree .so would silently mis-read the argument structs
+        raise RuntimeError(f"{_LIB_PATH} has ABI version {lib.vgpa_abi_version()}, the bindings expect {ABI_VERSION}: "
+                           "rebuild it with `python -m videogpa_b200.build`")
     _lib = lib
     return lib
 
