@@ -65,6 +65,8 @@ def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int 
     acc, clip = int(config.get("accumulate_grad_batches", 1)), config.get("gradient_clip_val")
     ddp = dist.is_available() and dist.is_initialized()
     gstep, micro, last, val_hist = 0, 0, float("nan"), []
+    import time
+    t_start, world = time.time(), (dist.get_world_size() if ddp else 1)
     opt.zero_grad(set_to_none=True)
     for epoch in range(int(config.get("max_epochs", 1))):
         for batch in train_loader:
@@ -84,7 +86,12 @@ def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int 
             gstep += 1
             if rank == 0 and gstep % int(config.get("log_every_n_steps", 10)) == 0:
                 out = step.last_output
-                log(f"step {gstep}: train/loss {last:.5f} reward_margin {float(out.reward_margin):.5f} lr {sched.get_last_lr()[0]:.3e}")
+                # the scalars the reference logs (:169-186): loss, reward margin / accuracy, stats/samples_per_sec (global_step x
+                # devices x batch_size over wall time) and stats/max_memory_gb
+                sps = gstep * world * int(config["batch_size"]) / max(1e-9, time.time() - t_start)
+                log(f"step {gstep}: train/loss {last:.5f} train/reward_margin {float(out.reward_margin):.5f} "
+                    f"train/reward_accuracy {float((out.reward_margin > 0).float().mean()):.2f} lr {sched.get_last_lr()[0]:.3e} "
+                    f"stats/samples_per_sec {sps:.4f} stats/max_memory_gb {torch.cuda.max_memory_reserved() / 1024 ** 3:.1f}")
             if gstep >= int(config["max_steps"]):
                 break
         if val_loader is not None:
