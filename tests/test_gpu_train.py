@@ -339,3 +339,46 @@ def test_transpose_kernel_bit_exact(lib, M, C_, ld):
     out = _t_rows(x)
     Mp = (M + 7) // 8 * 8
     assert out.shape == (C_, Mp) and torch.equal(out[:, :M], x.t()) and (Mp == M or float(out[:, M:].abs().max()) == 0.0)
+
+
+def test_i2v_training_step_with_image_condition(lib):
+    """train/CogVideoX-I2V-5B/03_train.py:114-148: the image condition (resize -> VAE encode -> sample x scaling_factor -> first
+    latent frame, zero frames after) is channel-concatenated to both noisy latents; the step differentiates to the LoRA factors."""
+    from oracle import dit_torch as O
+    from oracle import vae_torch as V
+    from videogpa_b200.train_dit import LoRATrainableTransformer
+    from videogpa_b200.train_step import DPOSharedStep
+    from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+    from videogpa_b200.vae import AutoencoderKLCogVideoXEncoder, VAEDecoderConfig
+    kw = dict(num_attention_heads=4, num_layers=2, text_embed_dim=256, sample_width=24, sample_height=16, sample_frames=9, max_text_seq_length=18,
+              in_channels=32, use_learned_positional_embeddings=True)
+    sd = {k: v.to(BF).float() for k, v in O.random_state_dict(O.DiTConfig(**kw), seed=10, randomize_norms=True, std=0.05).items()}
+    base = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
+    vcfg = VAEDecoderConfig(block_out_channels=(64, 64, 64, 128), sample_height=256, sample_width=384)
+    enc = AutoencoderKLCogVideoXEncoder(_bf16(V.random_encoder_state_dict(V.VAEConfig(block_out_channels=(64, 64, 64, 128)), seed=30)), vcfg, device="cuda")
+    pol = LoRATrainableTransformer(base, gradient_checkpointing="mlp")
+    with torch.no_grad():
+        for layer in pol.lora:
+            for m in layer:
+                layer[m][1].normal_(0, 0.02)
+    step = DPOSharedStep(base, None, beta=20.0, trainable=pol, vae_encoder=enc)
+    g = torch.Generator().manual_seed(5)
+    batch = {"x_win": torch.randn(2, 16, 3, 16, 24, generator=g), "x_lose": torch.randn(2, 16, 3, 16, 24, generator=g),
+             "prompt_emb": torch.randn(2, 18, 256, generator=g).to(BF), "image_emb": torch.rand(2, 3, 100, 150, generator=g) * 2 - 1}
+    x_win = batch["x_win"].cuda().permute(0, 2, 1, 3, 4).float()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    cond = step._image_condition(batch, x_win, gen)
+    assert cond.shape == x_win.shape and float(cond[:, 1:].abs().max()) == 0.0 and float(cond[:, 0].abs().max()) > 0
+    img = torch.nn.functional.interpolate(batch["image_emb"].cuda().float(), size=(128, 192))
+    want = enc.encode(img.unsqueeze(2).to(BF)).latent_dist.sample(generator=torch.Generator(device="cuda").manual_seed(3)) * 0.7
+    assert torch.equal(cond[:, 0], want[:, :, 0].float())                      # [B, C, 1, h, w] -> first latent frame
+    del batch["image_emb"]
+    assert float(step._image_condition(batch, x_win).abs().max()) == 0.0       # no image: zeros_like
+    batch["image_emb"] = torch.rand(2, 3, 100, 150, generator=g) * 2 - 1
+    loss = step.training_step(batch, generator=torch.Generator(device="cuda").manual_seed(9))
+    loss.backward()
+    assert torch.isfinite(loss) and all(p.grad is not None and torch.isfinite(p.grad).all() for p in pol.parameters())
+
+
+def _bf16(sd):
+    return {k: v.to(BF).float() for k, v in sd.items()}

@@ -22,11 +22,12 @@ from .schedulers import CogVideoXDPMScheduler
 
 
 class DPOSharedStep:
-    def __init__(self, transformer, ref_transformer, beta: float = 1.0, scheduler=None, trainable=None):
+    def __init__(self, transformer, ref_transformer, beta: float = 1.0, scheduler=None, trainable=None, vae_encoder=None):
         """transformer / ref_transformer: policy and reference for the forward-only path (validation_step). trainable: a
         train_dit.LoRATrainableTransformer — the policy of training_step; its frozen base doubles as the reference model."""
         self.transformer, self.ref_transformer = transformer, ref_transformer
         self.trainable = trainable
+        self.vae_encoder = vae_encoder            # I2V: encodes batch["image_emb"] into the first-frame condition
         self.scheduler = scheduler or CogVideoXDPMScheduler()
         self.loss_fn = create_loss_strategy(strategy="dpo", beta=beta)
         self.device = transformer.device
@@ -43,12 +44,33 @@ class DPOSharedStep:
             noise = torch.randn(x_win.shape, device=dev, generator=generator)
         x_win_noisy = self.scheduler.add_noise(x_win, noise, timesteps)
         x_lose_noisy = self.scheduler.add_noise(x_lose, noise, timesteps)
+        if self.transformer.config.in_channels == 2 * x_win.shape[2]:            # CogVideoX-5B-I2V: channel-concat the image condition
+            img_cond = self._image_condition(batch, x_win, generator)
+            x_win_noisy = torch.cat([x_win_noisy, img_cond], dim=2)
+            x_lose_noisy = torch.cat([x_lose_noisy, img_cond], dim=2)
         pair = torch.cat([x_win_noisy, x_lose_noisy], dim=0)                     # one batch of 2B per model
         emb2 = torch.cat([prompt_emb, prompt_emb], dim=0)
         t2 = torch.cat([timesteps, timesteps], dim=0)
         v_win_target = self.scheduler.get_velocity(x_win, noise, timesteps)
         v_lose_target = self.scheduler.get_velocity(x_lose, noise, timesteps)
         return B, pair, emb2, t2, v_win_target.contiguous(), v_lose_target.contiguous()
+
+    @torch.no_grad()
+    def _image_condition(self, batch: dict, x_win: torch.Tensor, generator=None) -> torch.Tensor:
+        """`img_cond` of train/CogVideoX-I2V-5B/03_train.py:119-130: the conditioning image resized to 8x the latent grid,
+        VAE-encoded, sampled, times scaling_factor, as the first latent frame followed by zero frames; zeros without an image."""
+        image_emb = batch.get("image_emb")
+        if image_emb is None:
+            return torch.zeros_like(x_win)
+        if self.vae_encoder is None:
+            raise RuntimeError("batch['image_emb'] needs vae_encoder=AutoencoderKLCogVideoXEncoder(...) (videogpa_b200.vae)")
+        B, Fr, C, h, w = x_win.shape
+        img = torch.nn.functional.interpolate(image_emb.to(self.device).float(), size=(h * 8, w * 8))
+        dist = self.vae_encoder.encode(img.unsqueeze(2).to(self.vae_encoder.dtype)).latent_dist
+        lat = dist.sample(generator=generator) * self.vae_encoder.config.scaling_factor      # [B, C, 1, h, w]
+        cond = torch.zeros_like(x_win)
+        cond[:, :1] = lat.permute(0, 2, 1, 3, 4).to(cond.dtype)
+        return cond
 
     @torch.no_grad()
     def _shared_step(self, batch: dict, generator=None, timesteps=None, noise=None) -> LossOutput:
