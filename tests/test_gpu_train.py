@@ -25,7 +25,7 @@ def _attn_ref(q, k, v, d_out, H, scale):
     return back(o.detach()), lse2.detach(), back(qf.grad), back(kf.grad), back(vf.grad)
 
 
-@pytest.mark.parametrize("B,H,Sq,Skv", [(1, 2, 128, 128), (2, 3, 300, 300), (1, 2, 200, 450)])
+@pytest.mark.parametrize("B,H,Sq,Skv", [(1, 2, 128, 128), (2, 3, 300, 300), (1, 2, 200, 450), (1, 1, 40, 40), (1, 2, 64, 65), (1, 1, 1, 193), (1, 1, 385, 8)])
 def test_attention_backward_vs_autograd(lib, B, H, Sq, Skv):
     from videogpa_b200 import dense
     g = torch.Generator().manual_seed(5)
