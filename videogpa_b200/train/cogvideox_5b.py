@@ -7,7 +7,8 @@ with generator seed 42, batch_size 1), :252-280 (DDP, bf16, max_steps, accumulat
 limit_val_batches 50, validation every epoch), :287 (`save_pretrained(out / "final_lora")`).
 
 One process per GPU (launch with torchrun for `devices` > 1): every rank runs its shard of the pairs and the LoRA gradients
-are averaged over NCCL (parallel.average_gradients). Logging is stdout (wandb is outside). `--synthetic N` swaps the 5B
+are averaged over NCCL (parallel.average_gradients). Logging is stdout (wandb is outside). A checkpoint whose transformer has
+in_channels 32 (CogVideoX-5B-I2V, `train/CogVideoX-I2V-5B/03_train.py`) gets the VAE encoder for the image condition. `--synthetic N` swaps the 5B
 checkpoint for an N-block random-weight transformer so the loop can be exercised without weights.
 """
 from __future__ import annotations
@@ -137,7 +138,7 @@ def main_train(config: dict, synthetic_layers: int = 0) -> dict:
     val_loader = DataLoader(val_ds, batch_size=1, shuffle=False, collate_fn=collate_fn) if len(val_ds) else None
 
     if synthetic_layers:
-        cfg = TransformerConfig.cogvideox_5b()
+        cfg = TransformerConfig.cogvideox_5b_i2v() if config.get("synthetic_variant") == "i2v" else TransformerConfig.cogvideox_5b()
         cfg.num_layers = synthetic_layers
         transformer = CogVideoXTransformer3D.random_init(cfg, seed=1234, device=device)
     else:
@@ -154,7 +155,23 @@ def main_train(config: dict, synthetic_layers: int = 0) -> dict:
         raise RuntimeError("only the reference's LoRA setup is supported: to_q / to_k / to_v / to_out.0, dropout 0")
     pol = LoRATrainableTransformer(transformer, r=config["lora_rank"], lora_alpha=config["lora_alpha"],
                                    gradient_checkpointing=bool(config.get("enable_gradient_checkpointing", True)))
-    step = DPOSharedStep(transformer, None, beta=config["beta"], trainable=pol)
+    vae_encoder = None
+    if transformer.config.in_channels == 32:            # CogVideoX-5B-I2V (train/CogVideoX-I2V-5B/03_train.py): image condition
+        from ..vae import AutoencoderKLCogVideoXEncoder, VAEDecoderConfig
+        if synthetic_layers:
+            vae_encoder = AutoencoderKLCogVideoXEncoder.random_init(VAEDecoderConfig(), seed=6, device=device)
+        else:
+            import json
+            from ..generate.cogvideox_5b import _load_safetensors_dir
+            vcfg = json.loads((Path(config["model_path"]) / "vae" / "config.json").read_text())
+            vknown = VAEDecoderConfig.__dataclass_fields__.keys()
+            vkw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in vcfg.items() if k in vknown}
+            vae_encoder = AutoencoderKLCogVideoXEncoder(_load_safetensors_dir(Path(config["model_path"]) / "vae"), VAEDecoderConfig(**vkw), device=device)
+        if config.get("enable_slicing"):
+            vae_encoder.enable_slicing()
+        if config.get("enable_tiling"):
+            vae_encoder.enable_tiling()
+    step = DPOSharedStep(transformer, None, beta=config["beta"], trainable=pol, vae_encoder=vae_encoder)
     res = fit(step, train_loader, config, val_loader=val_loader, rank=rank)
     if rank == 0:
         pol.save_pretrained(str(out_p / "final_lora"))
