@@ -32,7 +32,7 @@ def test_binding_table_matches_header():
 
 
 def test_loads_without_gpu_and_reports_errors(lib):
-    assert lib.vgpa_abi_version() == 2
+    assert lib.vgpa_abi_version() == _lib.ABI_VERSION
     # argument validation happens before any CUDA call, so it is checkable on a CPU-only host
     rc = lib.vgpa_linear_bf16(None, None)
     assert rc != 0 and b"null args" in lib.vgpa_last_error()
@@ -57,3 +57,18 @@ def test_product_path_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f"{f} imports the oracle"
+
+
+def test_graft_entry_build_hook_runs():
+    # the driver calls __graft_entry__.build() on a CPU-only host every round
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    ge = importlib.import_module("__graft_entry__")
+    ge.build()
+
+
+def test_header_abi_version_matches_bindings():
+    text = open(os.path.join(ROOT, "include", "videogpa_b200.h")).read()
+    m = re.search(r"#define\s+VGPA_ABI_VERSION\s+(\d+)", text)
+    assert m and int(m.group(1)) == _lib.ABI_VERSION
