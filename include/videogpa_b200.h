@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-#define VGPA_ABI_VERSION 2 /* 2: vgpa_attention_args gained `lse`; backward / training, T5 and transpose entry points added */
+#define VGPA_ABI_VERSION 3 /* 2: vgpa_attention_args gained `lse`; backward / training, T5 and transpose entry points added
+                              3: vgpa_attention_args gained `workspace` (bounded-softmax fast path of the head_dim-64 forward) */
 
 /* ------------------------------------------------------------------------------------------------
  * runtime
@@ -97,8 +98,16 @@ typedef struct vgpa_attention_args {
   int64_t q_batch_stride, k_batch_stride, v_batch_stride, out_batch_stride; /* elements */
   float* lse;      /* optional [B, H, Sq] fp32: log2-domain logsumexp of the scaled scores, saved for
                       vgpa_attention_bwd_bf16 (head_dim 64 only); NULL = not written */
+  /* Optional device scratch of vgpa_attention_workspace_bytes(B, H, head_dim) bytes, 16-byte aligned. With it the
+   * head_dim-64 forward first measures max|q|, max|k| per (batch, head) and serves every head whose score bound
+   * max|q| max|k| scale log2(e) is <= 90 with the bounded-softmax kernel (softmax shifted by a fixed per-head offset
+   * instead of the running row maximum: same function, no row statistics; attention_d64b_sm100.cu); the remaining
+   * heads, and every head when workspace is NULL, take the exact online-softmax kernel. */
+  void* workspace;
+  size_t workspace_bytes;
 } vgpa_attention_args;
 
+size_t vgpa_attention_workspace_bytes(int B, int H, int head_dim);
 int vgpa_attention_bf16(const vgpa_attention_args* args, void* stream);
 
 /* Backward of vgpa_attention_bf16 (head_dim 64) — the DPO training step differentiates through

@@ -44,7 +44,7 @@ def test_loads_without_gpu_and_reports_errors(lib):
 
 def test_struct_layouts_match_header_sizes():
     # spot-check ctypes struct sizes against the C layout rules (8-byte pointers, natural alignment)
-    assert ctypes.sizeof(_lib.AttentionArgs) == 4 * 8 + 5 * 4 + 4 + 8 * 8 + 8          # ... + lse pointer
+    assert ctypes.sizeof(_lib.AttentionArgs) == 4 * 8 + 5 * 4 + 4 + 8 * 8 + 8 + 16     # ... + lse pointer + workspace
     assert ctypes.sizeof(_lib.AttentionBwdArgs) == 9 * 8 + 5 * 4 + 4 + 16 * 8 + 8 + 8
     assert ctypes.sizeof(_lib.SchedArgs) == 7 * 8 + 8 + 4 + 7 * 4
     assert ctypes.sizeof(_lib.DpoArgs) % 8 == 0

@@ -43,6 +43,7 @@ class AttentionArgs(C.Structure):
         ("q_row_stride", c_i64), ("k_row_stride", c_i64), ("v_row_stride", c_i64), ("out_row_stride", c_i64),
         ("q_batch_stride", c_i64), ("k_batch_stride", c_i64), ("v_batch_stride", c_i64), ("out_batch_stride", c_i64),
         ("lse", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -135,6 +136,7 @@ SIGNATURES = {
     "vgpa_device_sm_count": (c_int, []),
     "vgpa_linear_bf16": (c_int, [C.POINTER(LinearArgs), c_void_p]),
     "vgpa_attention_bf16": (c_int, [C.POINTER(AttentionArgs), c_void_p]),
+    "vgpa_attention_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
     "vgpa_attention_bwd_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
     "vgpa_attention_bwd_bf16": (c_int, [C.POINTER(AttentionBwdArgs), c_void_p]),
     "vgpa_layernorm_modulate_bwd_bf16": (c_int, [C.POINTER(LayerNormArgs), c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
@@ -184,7 +186,7 @@ def lib_path() -> Path:
     return _LIB_PATH
 
 
-ABI_VERSION = 2          # VGPA_ABI_VERSION of include/videogpa_b200.h
+ABI_VERSION = 3          # VGPA_ABI_VERSION of include/videogpa_b200.h
 
 
 def load():

@@ -59,6 +59,7 @@ struct AttnParams {
   float scale_log2;
   float* lse;          // optional [B, H, Sq]: log2-domain logsumexp of the scaled scores (for the backward kernels)
   int H;
+  const float* bounds; // non-null: the bounded-softmax kernel runs too; skip the (batch, head)s it serves
 };
 
 using namespace attn;
@@ -132,6 +133,7 @@ attn_fwd_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int batch = blockIdx.z;
   const int m0 = blockIdx.x * (2 * AT_BM);
   const int nkv = (prm.Skv + AT_BN - 1) / AT_BN;
+  if (prm.bounds != nullptr && bounded_m(prm.bounds, batch * prm.H + head, prm.scale_log2) <= kBoundedMax) return;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
@@ -432,8 +434,12 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 namespace vgpa {
 int launch_attention_d128(const vgpa_attention_args* a, cudaStream_t stream);
-int launch_attention_d64x4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const vgpa_attention_args* a,
-                           int npoly, cudaStream_t stream);
+size_t attention_d64_workspace_bytes(int B, int H);
+int launch_attention_d64_bounded(const vgpa_attention_args* a, float* bounds, float scale_log2, int npoly8, cudaStream_t stream);
+}
+
+extern "C" size_t vgpa_attention_workspace_bytes(int B, int H, int head_dim) {
+  return head_dim == 64 ? vgpa::attention_d64_workspace_bytes(B, H) : 0;
 }
 
 extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
@@ -480,6 +486,7 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
   prm.Skv = a->Skv;
   prm.lse = a->lse;
   prm.H = a->H;
+  prm.bounds = nullptr;
   const float scale = a->scale > 0.f ? a->scale : 0.125f;
   prm.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((a->Sq + 2 * AT_BM - 1) / (2 * AT_BM), a->H, a->B);
@@ -490,13 +497,24 @@ extern "C" int vgpa_attention_bf16(const vgpa_attention_args* a, void* stream) {
     const char* e = getenv("VGPA_ATTN_NPOLY");
     npoly = e ? atoi(e) : 16;
   }
-  // Development knob: 1 = four softmax warpgroups (attention_d64x4_sm100.cu; same speed, measured), 0 (default) = two (this file).
-  static int x4 = -1;
-  if (x4 < 0) {
-    const char* e = getenv("VGPA_ATTN_X4");
-    x4 = e ? atoi(e) : 0;
+  // Bounded-softmax fast path (attention_d64b_sm100.cu) when the caller provides the scratch for the |q|, |k| bounds.
+  // Development knobs: VGPA_ATTN_FAST=0 forces the exact kernel, VGPA_ATTN_NPOLY8 = FMA-pipe share of the exponentials in 8ths.
+  static int fast = -1, npoly8 = 4;
+  if (fast < 0) {
+    const char* e = getenv("VGPA_ATTN_FAST");
+    fast = e ? atoi(e) : 1;
+    const char* e8 = getenv("VGPA_ATTN_NPOLY8");
+    if (e8) npoly8 = atoi(e8);
   }
-  if (x4 && a->lse == nullptr) return launch_attention_d64x4(tq, tk, tv, a, npoly, s);
+  if (fast && a->workspace != nullptr) {
+    VGPA_CHECK(a->workspace_bytes >= attention_d64_workspace_bytes(a->B, a->H),
+               "vgpa_attention_bf16: workspace too small (%zu bytes, need %zu)", a->workspace_bytes,
+               attention_d64_workspace_bytes(a->B, a->H));
+    VGPA_CHECK((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "vgpa_attention_bf16: workspace must be 16-byte aligned");
+    float* bounds = static_cast<float*>(a->workspace);
+    if (int rc = launch_attention_d64_bounded(a, bounds, prm.scale_log2, npoly8, s)) return rc;
+    prm.bounds = bounds;
+  }
   switch (npoly) {
     case 0: return launch_attn<0>(tq, tk, tv, prm, grid, s);
     case 32: return launch_attn<32>(tq, tk, tv, prm, grid, s);

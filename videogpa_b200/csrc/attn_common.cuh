@@ -64,6 +64,14 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
   p1 = __int_as_float((__float_as_int(r1) << 23) + __float_as_int(q1));
 }
 
+// Bounded-softmax dispatch (attention_d64b_sm100.cu): M = ceil(max|q| max|k| |scale log2e| + 0.5) of a (batch, head) from the
+// pre-pass buffer {max|q|^2, max|k|^2}. Heads with M <= kBoundedMax are served by the bounded kernel, the rest by the
+// exact online-softmax kernel; both kernels evaluate this same expression.
+constexpr float kBoundedMax = 90.0f;
+__device__ __forceinline__ float bounded_m(const float* bounds, int bh, float scale_log2) {
+  return ceilf(sqrtf(bounds[2 * bh]) * sqrtf(bounds[2 * bh + 1]) * fabsf(scale_log2) + 0.5f);
+}
+
 // NPOLY of the 64 column pairs of a row take the polynomial path, spread evenly.
 template <int NPOLY>
 __host__ __device__ constexpr bool pair_uses_poly(int pi) {

@@ -81,13 +81,30 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *
     return out
 
 
+_ATTN_WS: dict = {}
+
+
+def _attention_workspace(lib, B: int, heads: int, head_dim: int, device) -> torch.Tensor | None:
+    """Per-(device, stream) scratch for the |q|, |k| bounds of the bounded-softmax forward (head_dim 64)."""
+    n = lib.vgpa_attention_workspace_bytes(B, heads, head_dim)
+    if n == 0:
+        return None
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ATTN_WS.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 4096), dtype=torch.uint8, device=device)
+        _ATTN_WS[key] = ws
+    return ws
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
               out: torch.Tensor | None = None, scale: float = 0.0, head_dim: int = 64,
-              lse: torch.Tensor | None = None) -> torch.Tensor:
+              lse: torch.Tensor | None = None, exact: bool = False) -> torch.Tensor:
     """softmax(q k^T * scale) v with heads packed along the last dim.
 
     q: [B, Sq, >=heads*64] view, k/v: [B, Skv, >=heads*64] views (last dim contiguous; they may be
     column slices of one fused qkv buffer). Returns [B, Sq, heads*64] bf16.
+    exact=True withholds the workspace, which forces the online-softmax kernel for every head.
     """
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -110,6 +127,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
         if tuple(lse.shape) != (B, heads, Sq):
             raise RuntimeError(f"attention: lse must be [{B}, {heads}, {Sq}]")
         a.lse = lse.data_ptr()
+    ws = None if exact else _attention_workspace(lib, B, heads, head_dim, q.device)
+    if ws is not None:
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     _lib.check(lib.vgpa_attention_bf16(C.byref(a), _lib.current_stream()), "vgpa_attention_bf16")
     return out
 

@@ -57,7 +57,10 @@ def generate(args):
     print(f"Generating {len(tasks)} prompts, seed={args.seed}")
     output_root = Path(args.output_dir)
     output_root.mkdir(parents=True, exist_ok=True)
-    max_len = pipe.transformer.config.max_text_seq_length
+    # The reference calls pipe(...) without max_sequence_length, so diffusers pads prompts to its default of 226 tokens
+    # (train/CogVideoX1.5-5B/02_encode.py uses max_length=226 too). T5 runs unmasked, so the pad count changes every token:
+    # config.max_text_seq_length (224 for 1.5) only sizes a learned positional embedding, which 1.5 does not have.
+    max_len = 226
     negative = prompts("", max_len)
     for idx, item in enumerate(tasks):
         text_prompt = item.get("text_prompt", item.get("prompt", "")).strip()

@@ -35,6 +35,20 @@ def shard_round_robin(items, rank: int, world: int):
     return list(items)[rank::world]
 
 
+def shard_padded(items, rank: int, world: int):
+    """Training shard with the size rule of torch.utils.data.DistributedSampler (drop_last=False), which Lightning's DDP
+    strategy wraps around the reference's train loader (train/CogVideoX-5B/03_train.py:251,258-266): the index list is padded
+    to a multiple of `world` by wrapping around to its start, then rank r takes r, r+world, ... Every rank gets exactly
+    ceil(n / world) items, so all ranks run the same number of micro-batches and issue the same number of all-reduces."""
+    items = list(items)
+    if not items:
+        return []
+    total = -(-len(items) // world) * world
+    pad = total - len(items)
+    items = items + (items * (pad // len(items) + 1))[:pad]
+    return items[rank:total:world]
+
+
 def shard_contiguous(items, rank: int, world: int):
     """Scorer shard: contiguous chunks, remainder spread over the first ranks (replicate_scorer.py:244-250)."""
     items = list(items)

@@ -55,46 +55,63 @@ def split_dataset(ds, seed: int = 42):
     return random_split(ds, [n_train, len(ds) - n_train], generator=torch.Generator().manual_seed(seed))
 
 
-def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int = 0) -> dict:
+def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int = 0, checkpoint_fn=None) -> dict:
     """The loop `trainer.fit` runs around training_step: gradient accumulation, clipping, AdamW + cosine warm-up schedule per
-    optimizer step, DDP gradient average, validation (at most 50 batches) after every epoch. -> {"steps", "last_loss", "val"}."""
+    optimizer step, DDP gradient average, validation (at most 50 batches) after every epoch. -> {"steps", "last_loss", "val"}.
+
+    Stopping rule: the reference passes only `max_steps` to pl.Trainer (:258-266), so Lightning sets max_epochs = -1 and
+    training runs until `max_steps` optimizer steps; `max_epochs` of the config is not a stopping criterion there and is
+    ignored here too. Like Lightning, a partial accumulation window is flushed (stepped) on the last batch of an epoch; every
+    rank must see the same number of micro-batches per epoch (main_train pads the shards like DistributedSampler), so all
+    ranks issue the same sequence of all-reduces. `checkpoint_fn(gstep, val_loss)` is called on rank 0 every
+    `checkpoint_every_n_steps` optimizer steps (ModelCheckpoint(every_n_train_steps=...), :267-274)."""
+    import time
     import torch.distributed as dist
     from ..parallel import average_gradients
     opt = step.configure_optimizers(lr=config["learning_rate"])
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: cosine_schedule_with_warmup(s, config.get("warmup_steps", 500), config["max_steps"]))
     params = step.trainable.parameters()
     acc, clip = int(config.get("accumulate_grad_batches", 1)), config.get("gradient_clip_val")
+    max_steps = int(config["max_steps"])
+    ckpt_every = int(config.get("checkpoint_every_n_steps", 0) or 0)
     ddp = dist.is_available() and dist.is_initialized()
-    gstep, micro, last, val_hist = 0, 0, float("nan"), []
-    import time
+    gstep, last, val_hist, epoch = 0, float("nan"), [], 0
     t_start, world = time.time(), (dist.get_world_size() if ddp else 1)
     opt.zero_grad(set_to_none=True)
-    for epoch in range(int(config.get("max_epochs", 1))):
-        for batch in train_loader:
+
+    def optimizer_step():
+        nonlocal gstep
+        if ddp:
+            average_gradients(params)
+        if clip:
+            torch.nn.utils.clip_grad_norm_(params, float(clip))
+        opt.step()
+        sched.step()
+        opt.zero_grad(set_to_none=True)
+        gstep += 1
+        if rank == 0 and gstep % int(config.get("log_every_n_steps", 10)) == 0:
+            out = step.last_output
+            # the scalars the reference logs (:169-186): loss, reward margin / accuracy, stats/samples_per_sec (global_step x
+            # devices x batch_size over wall time) and stats/max_memory_gb
+            sps = gstep * world * int(config["batch_size"]) / max(1e-9, time.time() - t_start)
+            log(f"step {gstep}: train/loss {last:.5f} train/reward_margin {float(out.reward_margin):.5f} "
+                f"train/reward_accuracy {float((out.reward_margin > 0).float().mean()):.2f} lr {sched.get_last_lr()[0]:.3e} "
+                f"stats/samples_per_sec {sps:.4f} stats/max_memory_gb {(torch.cuda.max_memory_reserved() if torch.cuda.is_available() else 0) / 1024 ** 3:.1f}")
+        if rank == 0 and checkpoint_fn is not None and ckpt_every and gstep % ckpt_every == 0:
+            checkpoint_fn(gstep, val_hist[-1] if val_hist else float("nan"))
+
+    while gstep < max_steps:
+        n_batches = len(train_loader)
+        if n_batches == 0:
+            raise RuntimeError("fit: the training loader is empty")
+        for bi, batch in enumerate(train_loader):
             loss = step.training_step(batch)
             (loss / acc).backward()                     # Lightning divides the loss by accumulate_grad_batches
             last = float(loss.detach())
-            micro += 1
-            if micro % acc:
-                continue
-            if ddp:
-                average_gradients(params)
-            if clip:
-                torch.nn.utils.clip_grad_norm_(params, float(clip))
-            opt.step()
-            sched.step()
-            opt.zero_grad(set_to_none=True)
-            gstep += 1
-            if rank == 0 and gstep % int(config.get("log_every_n_steps", 10)) == 0:
-                out = step.last_output
-                # the scalars the reference logs (:169-186): loss, reward margin / accuracy, stats/samples_per_sec (global_step x
-                # devices x batch_size over wall time) and stats/max_memory_gb
-                sps = gstep * world * int(config["batch_size"]) / max(1e-9, time.time() - t_start)
-                log(f"step {gstep}: train/loss {last:.5f} train/reward_margin {float(out.reward_margin):.5f} "
-                    f"train/reward_accuracy {float((out.reward_margin > 0).float().mean()):.2f} lr {sched.get_last_lr()[0]:.3e} "
-                    f"stats/samples_per_sec {sps:.4f} stats/max_memory_gb {torch.cuda.max_memory_reserved() / 1024 ** 3:.1f}")
-            if gstep >= int(config["max_steps"]):
-                break
+            if (bi + 1) % acc == 0 or bi + 1 == n_batches:   # accumulation windows restart every epoch; the last one may be short
+                optimizer_step()
+                if gstep >= max_steps:
+                    break
         if val_loader is not None:
             tot, n = 0.0, 0
             for k, vb in enumerate(val_loader):
@@ -106,14 +123,34 @@ def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int 
                 val_hist.append(tot / n)
                 if rank == 0:
                     log(f"epoch {epoch}: val/loss {tot / n:.5f}")
-        if gstep >= int(config["max_steps"]):
-            break
-    return {"steps": gstep, "last_loss": last, "val": val_hist}
+        epoch += 1
+    return {"steps": gstep, "last_loss": last, "val": val_hist, "epochs": epoch}
+
+
+class TopKCheckpoints:
+    """ModelCheckpoint(monitor="val/loss", mode="min", save_top_k=k, every_n_train_steps=n) of the reference (:267-274):
+    every call writes `<dir>/step=<N>-val_loss=<v>` with `save_fn` and keeps the k entries with the lowest monitored value
+    (entries saved before the first validation carry NaN and are the first to go)."""
+
+    def __init__(self, directory, save_fn, top_k: int = 10):
+        self.dir, self.save_fn, self.top_k, self.kept = Path(directory), save_fn, int(top_k), []
+
+    def __call__(self, gstep: int, val_loss: float):
+        import shutil
+        path = self.dir / (f"step={gstep}-val_loss={val_loss:.4f}" if val_loss == val_loss else f"step={gstep}")
+        self.save_fn(str(path))
+        self.kept.append((val_loss if val_loss == val_loss else float("inf"), gstep, path))
+        if self.top_k >= 0 and len(self.kept) > self.top_k:
+            self.kept.sort(key=lambda e: (e[0], -e[1]))
+            for _, _, old in self.kept[self.top_k:]:
+                shutil.rmtree(old, ignore_errors=True)
+            self.kept = self.kept[:self.top_k]
+        return path
 
 
 def main_train(config: dict, synthetic_layers: int = 0) -> dict:
     from ..dataset import DPODataset, collate_fn
-    from ..parallel import init_from_env, shard_round_robin
+    from ..parallel import init_from_env, shard_padded
     from ..train_dit import LoRATrainableTransformer
     from ..train_step import DPOSharedStep
     from ..transformer import CogVideoXTransformer3D, TransformerConfig
@@ -131,8 +168,8 @@ def main_train(config: dict, synthetic_layers: int = 0) -> dict:
                       metric_name=config.get("metric_name", "consistency_score"), metric_mode=config.get("metric_mode", "min"),
                       min_gap=config.get("min_gap", 0.05), motion_threshold=config.get("motion_threshold", 0.001))
     train_ds, val_ds = split_dataset(full)
-    if world > 1:                                       # DistributedSampler's job: a disjoint shard per rank
-        train_ds = torch.utils.data.Subset(train_ds, shard_round_robin(range(len(train_ds)), rank, world))
+    if world > 1:                                       # DistributedSampler's job: equal-sized shards, padded by wrapping around
+        train_ds = torch.utils.data.Subset(train_ds, shard_padded(range(len(train_ds)), rank, world))
     train_loader = DataLoader(train_ds, batch_size=config["batch_size"], shuffle=True, collate_fn=collate_fn,
                               generator=torch.Generator().manual_seed(1234 + rank))
     val_loader = DataLoader(val_ds, batch_size=1, shuffle=False, collate_fn=collate_fn) if len(val_ds) else None
@@ -172,7 +209,8 @@ def main_train(config: dict, synthetic_layers: int = 0) -> dict:
         if config.get("enable_tiling"):
             vae_encoder.enable_tiling()
     step = DPOSharedStep(transformer, None, beta=config["beta"], trainable=pol, vae_encoder=vae_encoder)
-    res = fit(step, train_loader, config, val_loader=val_loader, rank=rank)
+    ckpt = TopKCheckpoints(out_p / "checkpoints", pol.save_pretrained, top_k=int(config.get("save_top_k", 10))) if rank == 0 else None
+    res = fit(step, train_loader, config, val_loader=val_loader, rank=rank, checkpoint_fn=ckpt)
     if rank == 0:
         pol.save_pretrained(str(out_p / "final_lora"))
         print(f"saved {out_p / 'final_lora'} after {res['steps']} optimizer steps")
