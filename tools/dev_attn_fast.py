@@ -91,8 +91,10 @@ if __name__ == "__main__":
     elif mode == "bench":
         bench()
     else:
-        for np8 in ("0", "2", "3", "4", "5"):
-            env = dict(os.environ, VGPA_ATTN_NPOLY8=np8)
-            if np8 == "4":
+        combos = [c.split(":") for c in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0:0", "3:0", "4:0", "4:1"])]
+        for i, (np8, dbg) in enumerate(combos):
+            env = dict(os.environ, VGPA_ATTN_NPOLY8=np8, VGPA_ATTN_DBG=dbg)
+            if i == 0 and os.environ.get("DEV_ATTN_REF"):
                 env["DEV_ATTN_ALL"] = "1"
+            print(f"--- NPOLY8={np8} DBG={dbg}", flush=True)
             subprocess.run([sys.executable, __file__, "bench"], env=env, check=False)
