@@ -62,7 +62,7 @@ struct FbParams {
   float* lse;
   int H;
   const float* bounds;   // [B*H][2]: max |q|^2, max |k|^2
-  int dbg;               // development: bit 0 = skip the row-sum MMAs (timing experiments only; results are then wrong)
+  int dbg;               // development: bit 0 = skip the row-sum MMAs (timing only; results are then wrong), bit 1 = TMA producer waits with a suspend hint
 };
 
 __device__ __forceinline__ uint64_t f2_fma_rm(uint64_t a, uint64_t b, uint64_t c) {
@@ -187,7 +187,8 @@ attn_fwd_d64_bounded_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         int slot = 0;
         uint32_t phase = 0;
         auto load = [&](const CUtensorMap* tm, int row0) {
-          ptx::mbar_wait(&kv_empty[slot], phase ^ 1);
+          if (prm.dbg & 2) ptx::mbar_wait_relaxed(&kv_empty[slot], phase ^ 1, 2000);
+          else ptx::mbar_wait(&kv_empty[slot], phase ^ 1);
           ptx::mbar_expect_tx(&kv_full[slot], FB_TILE_BYTES);
           ptx::tma_load_3d(sKV + slot * FB_TILE_BYTES, tm, &kv_full[slot], head * FB_D, row0, batch);
           if (++slot == FB_SLOTS) { slot = 0; phase ^= 1; }
@@ -271,63 +272,64 @@ attn_fwd_d64_bounded_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // row inside the Q tile
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + col_s(t) + hh * FB_HALF;
-    const uint32_t tP = tmem_base + lane_addr + col_p(t, hh);
+    const uint32_t tS = ptx::opaque(tmem_base + lane_addr + col_s(t) + hh * FB_HALF);
+    const uint32_t tP = ptx::opaque(tmem_base + lane_addr + col_p(t, hh));
+    const uint32_t a_s_full = ptx::opaque(ptx::smem_u32(&s_full[t]));
+    const uint32_t a_s_free = ptx::opaque(ptx::smem_u32(&s_free[t]));
+    const uint32_t a_p_ready = ptx::opaque(ptx::smem_u32(&p_ready[t * 2 + hh]));
+    const uint32_t a_pv_done = ptx::opaque(ptx::smem_u32(&pv_done[t * 2 + hh]));
     const float sc = prm.scale_log2;
     const uint64_t c2 = f2_pack(sc, sc);
     const uint64_t negm2 = f2_pack(-m_off, -m_off);
     const uint64_t a2 = f2_pack(12582912.0f - m_off, 12582912.0f - m_off);
     const int tail = prm.Skv - (nkv - 1) * FB_BN - hh * FB_HALF;   // valid columns of this half in the last kv tile
-    uint64_t* my_p_ready = &p_ready[t * 2 + hh];
-    uint64_t* my_pv_done = &pv_done[t * 2 + hh];
 
     uint32_t s0[16], s1[16], s2[16];
-    uint32_t pk[24];
+    uint32_t pk[16];
 
-    auto arrive_warp = [&](uint64_t* bar) {
+    auto arrive_warp = [&](uint32_t bar) {
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar);
+      if (lane == 0) ptx::mbar_arrive_a(bar);
     };
 
-    ptx::mbar_wait(&s_full[t], 0);
+    ptx::mbar_wait_a(a_s_full, 0);
     ptx::tc_fence_after();
     ptx::tmem_ld_32x16(tS, s0);
     ptx::tmem_ld_32x16(tS + 16, s1);
     ptx::tmem_ld_32x16(tS + 32, s2);
     ptx::tmem_ld_wait();
-    arrive_warp(&s_free[t]);
+    arrive_warp(a_s_free);
 
+    // One kv tile = three 16-column chunks. The P columns of chunks 0 and 1 go back to TMEM together once the PV product of
+    // tile j-1 has released the (single) P buffer of this half; that barrier and the one of the next S tile are probed one
+    // chunk early so that the probe latency is off the critical path. Chunks 0 and 1 of the next S tile stream in under chunk 2.
     for (int j = 0; j < nkv; ++j) {
       const bool last = (j == nkv - 1);
+      if (!last) exp_chunk<NP, false>(s0, &pk[0], c2, negm2, a2, 0, 0);
+      else exp_chunk<NP, true>(s0, &pk[0], c2, negm2, a2, 0, tail);
+      const bool pv_ok = j > 0 ? ptx::mbar_try_wait_a(a_pv_done, (j - 1) & 1) : true;
+      if (!last) exp_chunk<NP, false>(s1, &pk[8], c2, negm2, a2, 0, 0);
+      else exp_chunk<NP, true>(s1, &pk[8], c2, negm2, a2, 16, tail);
+      if (!pv_ok) ptx::mbar_wait_a(a_pv_done, (j - 1) & 1);     // P_(t,hh)(j-1) has been consumed
+      ptx::tc_fence_after();
+      ptx::tmem_st_32x16(tP, pk);
       if (!last) {
-        exp_chunk<NP, false>(s0, &pk[0], c2, negm2, a2, 0, 0);
-        exp_chunk<NP, false>(s1, &pk[8], c2, negm2, a2, 0, 0);
-      } else {
-        exp_chunk<NP, true>(s0, &pk[0], c2, negm2, a2, 0, tail);
-        exp_chunk<NP, true>(s1, &pk[8], c2, negm2, a2, 16, tail);
-      }
-      if (j > 0) {                                           // P_(t,hh)(j-1) has been consumed
-        ptx::mbar_wait(my_pv_done, (j - 1) & 1);
-        ptx::tc_fence_after();
-      }
-      ptx::tmem_st_32x16(tP, *reinterpret_cast<uint32_t (*)[16]>(&pk[0]));
-      if (!last) {                                           // first two chunks of S_t(j+1) stream in under chunk 2
-        ptx::mbar_wait(&s_full[t], (j + 1) & 1);
+        ptx::mbar_wait_a(a_s_full, (j + 1) & 1);
         ptx::tc_fence_after();
         ptx::tmem_ld_32x16(tS, s0);
         ptx::tmem_ld_32x16(tS + 16, s1);
-        exp_chunk<NP, false>(s2, &pk[16], c2, negm2, a2, 0, 0);
+        exp_chunk<NP, false>(s2, &pk[0], c2, negm2, a2, 0, 0);
       } else {
-        exp_chunk<NP, true>(s2, &pk[16], c2, negm2, a2, 32, tail);
+        exp_chunk<NP, true>(s2, &pk[0], c2, negm2, a2, 32, tail);
       }
-      ptx::tmem_st_32x8(tP + 16, *reinterpret_cast<uint32_t (*)[8]>(&pk[16]));
+      ptx::tmem_st_32x8(tP + 16, *reinterpret_cast<uint32_t (*)[8]>(&pk[0]));
       if (!last) ptx::tmem_ld_32x16(tS + 32, s2);
       ptx::tmem_st_wait();
-      arrive_warp(my_p_ready);
+      arrive_warp(a_p_ready);
       if (!last) {
         ptx::tmem_ld_wait();
-        arrive_warp(&s_free[t]);
+        arrive_warp(a_s_free);
       }
     }
 
