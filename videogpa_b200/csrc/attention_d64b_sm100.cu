@@ -213,7 +213,12 @@ attn_fwd_d64_bounded_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       // ring position of a tile in the sequence K_0, K_1, V_0, K_2, V_1, ..., K_{n-1}, V_{n-2}, V_{n-1}
       auto idx_k = [&](int j) { return j == 0 ? 0 : 2 * j - 1; };
       auto idx_v = [&](int j) { return j < nkv - 1 ? 2 * j + 2 : 2 * nkv - 1; };
-      auto wait_kv = [&](int idx) { ptx::mbar_wait(&kv_full[idx & (FB_SLOTS - 1)], (idx / FB_SLOTS) & 1); };
+      const bool relaxed = (prm.dbg & 4) != 0;
+      auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
+        if (relaxed) ptx::mbar_wait_relaxed(bar, parity, 1000);
+        else ptx::mbar_wait(bar, parity);
+      };
+      auto wait_kv = [&](int idx) { wait_bar(&kv_full[idx & (FB_SLOTS - 1)], (idx / FB_SLOTS) & 1); };
       if (ptx::elect_one()) {
         if (cw == 1) {
           const uint32_t sQ_a = ptx::smem_u32(sQ);
@@ -225,7 +230,7 @@ attn_fwd_d64_bounded_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             const uint64_t b = ptx::smem_desc_sw128(sKV_a + (idx & (FB_SLOTS - 1)) * FB_TILE_BYTES, 16, 1024);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-              if (j > 0) ptx::mbar_wait(&s_free[t], (j - 1) & 1);
+              if (j > 0) wait_bar(&s_free[t], (j - 1) & 1);
               ptx::tc_fence_after();
               const uint64_t a = ptx::smem_desc_sw128(sQ_a + t * FB_Q_BYTES, 16, 1024);
 #pragma unroll
@@ -247,7 +252,7 @@ attn_fwd_d64_bounded_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             const uint64_t b0 = ptx::smem_desc_sw128(sKV_a + (idx & (FB_SLOTS - 1)) * FB_TILE_BYTES, 1024, 1024);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              ptx::mbar_wait(&p_ready[t * 2 + hh], j & 1);
+              wait_bar(&p_ready[t * 2 + hh], j & 1);
               ptx::tc_fence_after();
               const uint32_t tp = tmem_base + (hh ? col_p(0, 1) + 32 * t : col_p(0, 0) + 128 * t);
 #pragma unroll
@@ -285,7 +290,7 @@ attn_fwd_d64_bounded_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const int tail = prm.Skv - (nkv - 1) * FB_BN - hh * FB_HALF;   // valid columns of this half in the last kv tile
 
     uint32_t s0[16], s1[16], s2[16];
-    uint32_t pk[16];
+    uint32_t pk[24];
 
     auto arrive_warp = [&](uint32_t bar) {
       ptx::tc_fence_before();
@@ -293,6 +298,14 @@ attn_fwd_d64_bounded_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       if (lane == 0) ptx::mbar_arrive_a(bar);
     };
 
+    if (t == 1) {
+      // Start Q tile 1 about half a kv tile late: the two tiles then ask the tensor pipe for their S / PV bursts at
+      // different times and the four warps of a sub-partition are in different parts of the tile body.
+      const long long t0 = clock64();
+      const int stagger = prm.dbg >> 8;
+      while (clock64() - t0 < stagger) {
+      }
+    }
     ptx::mbar_wait_a(a_s_full, 0);
     ptx::tc_fence_after();
     ptx::tmem_ld_32x16(tS, s0);
@@ -301,36 +314,40 @@ attn_fwd_d64_bounded_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     ptx::tmem_ld_wait();
     arrive_warp(a_s_free);
 
-    // One kv tile = three 16-column chunks. The P columns of chunks 0 and 1 go back to TMEM together once the PV product of
-    // tile j-1 has released the (single) P buffer of this half; that barrier and the one of the next S tile are probed one
-    // chunk early so that the probe latency is off the critical path. Chunks 0 and 1 of the next S tile stream in under chunk 2.
+    // One kv tile = three 16-column chunks. P stays in registers until the whole half row is done and goes back to TMEM in one
+    // burst: p_ready is only published then anyway, and the PV product of tile j-1, which must have released the (single) P
+    // buffer of this half, gets the whole tile to complete. Chunks 0 and 1 of the next S tile stream in under chunk 2; their
+    // barrier is probed (test_wait: never suspends) one chunk early so that the probe latency is off the critical path.
     for (int j = 0; j < nkv; ++j) {
       const bool last = (j == nkv - 1);
       if (!last) exp_chunk<NP, false>(s0, &pk[0], c2, negm2, a2, 0, 0);
       else exp_chunk<NP, true>(s0, &pk[0], c2, negm2, a2, 0, tail);
-      const bool pv_ok = j > 0 ? ptx::mbar_try_wait_a(a_pv_done, (j - 1) & 1) : true;
+      const bool s_ok = !last ? ptx::mbar_test_wait_a(a_s_full, (j + 1) & 1) : true;
       if (!last) exp_chunk<NP, false>(s1, &pk[8], c2, negm2, a2, 0, 0);
       else exp_chunk<NP, true>(s1, &pk[8], c2, negm2, a2, 16, tail);
-      if (!pv_ok) ptx::mbar_wait_a(a_pv_done, (j - 1) & 1);     // P_(t,hh)(j-1) has been consumed
-      ptx::tc_fence_after();
-      ptx::tmem_st_32x16(tP, pk);
+      bool pv_ok = true;
       if (!last) {
-        ptx::mbar_wait_a(a_s_full, (j + 1) & 1);
+        if (!s_ok) ptx::mbar_wait_a(a_s_full, (j + 1) & 1);
         ptx::tc_fence_after();
         ptx::tmem_ld_32x16(tS, s0);
         ptx::tmem_ld_32x16(tS + 16, s1);
-        exp_chunk<NP, false>(s2, &pk[0], c2, negm2, a2, 0, 0);
+        if (j > 0) pv_ok = ptx::mbar_test_wait_a(a_pv_done, (j - 1) & 1);
+        exp_chunk<NP, false>(s2, &pk[16], c2, negm2, a2, 0, 0);
+        ptx::tmem_ld_32x16(tS + 32, s2);
       } else {
-        exp_chunk<NP, true>(s2, &pk[0], c2, negm2, a2, 32, tail);
+        if (j > 0) pv_ok = ptx::mbar_test_wait_a(a_pv_done, (j - 1) & 1);
+        exp_chunk<NP, true>(s2, &pk[16], c2, negm2, a2, 32, tail);
       }
-      ptx::tmem_st_32x8(tP + 16, *reinterpret_cast<uint32_t (*)[8]>(&pk[0]));
-      if (!last) ptx::tmem_ld_32x16(tS + 32, s2);
-      ptx::tmem_st_wait();
-      arrive_warp(a_p_ready);
-      if (!last) {
+      if (!pv_ok) ptx::mbar_wait_a(a_pv_done, (j - 1) & 1);     // P_(t,hh)(j-1) has been consumed
+      ptx::tc_fence_after();
+      ptx::tmem_st_32x16(tP, *reinterpret_cast<uint32_t (*)[16]>(&pk[0]));
+      ptx::tmem_st_32x8(tP + 16, *reinterpret_cast<uint32_t (*)[8]>(&pk[16]));
+      if (!last) {                                            // S_t(j+2) is wanted sooner than the PV product: release S first
         ptx::tmem_ld_wait();
         arrive_warp(a_s_free);
       }
+      ptx::tmem_st_wait();
+      arrive_warp(a_p_ready);
     }
 
     // ---------------------------------------------------------- epilogue: O / l -> bf16 global (32 of the 64 columns)

@@ -89,6 +89,8 @@ def _attention_workspace(lib, B: int, heads: int, head_dim: int, device) -> torc
     n = lib.vgpa_attention_workspace_bytes(B, heads, head_dim)
     if n == 0:
         return None
+    if torch.cuda.is_current_stream_capturing():       # a captured launch keeps the pointer: give the graph its own buffer
+        return torch.empty(max(n, 4096), dtype=torch.uint8, device=device)
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     ws = _ATTN_WS.get(key)
     if ws is None or ws.numel() < n:
