@@ -45,35 +45,40 @@ class DiTConfig:
 
 
 def random_state_dict(cfg: DiTConfig, seed: int = 1234, dtype=torch.float32, std: float = 0.02,
-                      randomize_norms: bool = False) -> dict:
+                      randomize_norms: bool = False, device=None) -> dict:
     """SURVEY.md §8d synthetic weights: N(0, 0.02^2) for Linear/Conv, LayerNorm gamma 1 beta 0, biases 0.
 
     randomize_norms=True also perturbs norm affine params and biases so parity tests exercise them.
+    device: generate on that device (its own generator stream: CPU and CUDA draws differ), for the full-size GPU checks.
     """
-    g = torch.Generator().manual_seed(seed)
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    g = torch.Generator(device=device).manual_seed(seed)
     D, Tm = cfg.inner_dim, cfg.time_embed_dim
     sd = {}
 
+    def randn(*shape):
+        return torch.randn(*shape, generator=g, device=device)
+
     def lin(name, out_f, in_f, bias=True):
-        sd[name + ".weight"] = torch.randn(out_f, in_f, generator=g) * std
+        sd[name + ".weight"] = randn(out_f, in_f) * std
         if bias:
-            sd[name + ".bias"] = (torch.randn(out_f, generator=g) * std) if randomize_norms else torch.zeros(out_f)
+            sd[name + ".bias"] = (randn(out_f) * std) if randomize_norms else torch.zeros(out_f, device=device)
 
     def norm(name, n):
-        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(n, generator=g)) if randomize_norms else torch.ones(n)
-        sd[name + ".bias"] = (0.05 * torch.randn(n, generator=g)) if randomize_norms else torch.zeros(n)
+        sd[name + ".weight"] = (1.0 + 0.1 * randn(n)) if randomize_norms else torch.ones(n, device=device)
+        sd[name + ".bias"] = (0.05 * randn(n)) if randomize_norms else torch.zeros(n, device=device)
 
     p = cfg.patch_size
     if cfg.patch_size_t is None:
-        sd["patch_embed.proj.weight"] = torch.randn(D, cfg.in_channels, p, p, generator=g) * std
+        sd["patch_embed.proj.weight"] = randn(D, cfg.in_channels, p, p) * std
     else:
-        sd["patch_embed.proj.weight"] = torch.randn(D, cfg.in_channels * cfg.patch_size_t * p * p, generator=g) * std
-    sd["patch_embed.proj.bias"] = (torch.randn(D, generator=g) * std) if randomize_norms else torch.zeros(D)
+        sd["patch_embed.proj.weight"] = randn(D, cfg.in_channels * cfg.patch_size_t * p * p) * std
+    sd["patch_embed.proj.bias"] = (randn(D) * std) if randomize_norms else torch.zeros(D, device=device)
     lin("patch_embed.text_proj", D, cfg.text_embed_dim)
     if cfg.use_learned_positional_embeddings:
         n_tok = cfg.max_text_seq_length + ((cfg.sample_frames - 1) // cfg.temporal_compression_ratio + 1) * \
             (cfg.sample_height // p) * (cfg.sample_width // p)
-        sd["patch_embed.pos_embedding"] = torch.randn(1, n_tok, D, generator=g) * std
+        sd["patch_embed.pos_embedding"] = randn(1, n_tok, D) * std
     lin("time_embedding.linear_1", Tm, D)
     lin("time_embedding.linear_2", Tm, Tm)
     for i in range(cfg.num_layers):
@@ -125,12 +130,30 @@ def apply_rotary(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch
 
 def timestep_embedding(timesteps: torch.Tensor, dim: int) -> torch.Tensor:
     half = dim // 2
-    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / half
     emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)          # flip_sin_to_cos=True
 
 
 # ------------------------------------------------------------------ App. A.1 / A.2
+def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """F.scaled_dot_product_attention. For fp32 CUDA inputs (the full-size checks run this oracle on the GPU) the softmax is
+    written out over chunks of heads and queries, so that it is plain fp32 arithmetic with no fused-kernel precision choices
+    and bounded memory (the caller switches TF32 off)."""
+    if not (q.is_cuda and q.dtype == torch.float32):
+        return F.scaled_dot_product_attention(q, k, v)
+    B, Hh, S, d = q.shape
+    out = torch.empty_like(q)
+    rows = max(1, min(S, (1 << 28) // max(1, k.shape[2])))           # <= 1 GiB of fp32 scores per chunk
+    for b in range(B):
+        for h in range(Hh):
+            kt = k[b, h].t()
+            for r0 in range(0, S, rows):
+                p = torch.softmax((q[b, h, r0:r0 + rows] @ kt) * (d ** -0.5), dim=-1)
+                out[b, h, r0:r0 + rows] = p @ v[b, h]
+    return out
+
+
 def attention_block(sd, prefix, cfg, n_hs, n_enc, rope):
     Hh, d = cfg.num_attention_heads, cfg.attention_head_dim
     St = n_enc.shape[1]
@@ -145,7 +168,7 @@ def attention_block(sd, prefix, cfg, n_hs, n_enc, rope):
         cos, sin = rope
         q = torch.cat([q[:, :, :St], apply_rotary(q[:, :, St:], cos, sin)], dim=2)
         k = torch.cat([k[:, :, :St], apply_rotary(k[:, :, St:], cos, sin)], dim=2)
-    o = F.scaled_dot_product_attention(q, k, v)
+    o = sdpa(q, k, v)
     o = o.transpose(1, 2).reshape(B, S, Hh * d)
     o = F.linear(o, sd[prefix + "to_out.0.weight"], sd[prefix + "to_out.0.bias"])
     return o[:, St:], o[:, :St]

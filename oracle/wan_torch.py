@@ -40,17 +40,24 @@ class WanConfig:
         return self.dim // self.num_heads
 
 
-def random_state_dict(cfg: WanConfig, seed: int = 21, std: float = 0.02, dtype=torch.float32) -> dict:
-    g = torch.Generator().manual_seed(seed)
+def random_state_dict(cfg: WanConfig, seed: int = 21, std: float = 0.02, dtype=torch.float32, device=None) -> dict:
+    """device: generate on that device (its own generator stream), for the full-size GPU checks."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    g = torch.Generator(device=device).manual_seed(seed)
     sd = {}
 
+    class _R:                                   # torch.randn on `device` with the shared generator
+        @staticmethod
+        def randn(*shape, generator=None):
+            return torch.randn(*shape, generator=g, device=device)
+
     def lin(name, o, i, s=std):
-        sd[name + ".weight"] = (torch.randn(o, i, generator=g) * s).to(dtype)
-        sd[name + ".bias"] = (torch.randn(o, generator=g) * 0.02).to(dtype)
+        sd[name + ".weight"] = (_R.randn(o, i) * s).to(dtype)
+        sd[name + ".bias"] = (_R.randn(o) * 0.02).to(dtype)
 
     D = cfg.dim
-    sd["patch_embedding.weight"] = (torch.randn(D, cfg.in_dim, *cfg.patch_size, generator=g) * std).to(dtype)
-    sd["patch_embedding.bias"] = (torch.randn(D, generator=g) * 0.02).to(dtype)
+    sd["patch_embedding.weight"] = (_R.randn(D, cfg.in_dim, *cfg.patch_size) * std).to(dtype)
+    sd["patch_embedding.bias"] = (_R.randn(D) * 0.02).to(dtype)
     lin("text_embedding.0", D, cfg.text_dim); lin("text_embedding.2", D, D)
     lin("time_embedding.0", D, cfg.freq_dim); lin("time_embedding.2", D, D)
     lin("time_projection.1", 6 * D, D)
@@ -59,32 +66,32 @@ def random_state_dict(cfg: WanConfig, seed: int = 21, std: float = 0.02, dtype=t
         for a in ("self_attn", "cross_attn"):
             for m in ("q", "k", "v", "o"):
                 lin(b + f"{a}.{m}", D, D)
-            sd[b + f"{a}.norm_q.weight"] = (1 + 0.1 * torch.randn(D, generator=g)).to(dtype)
-            sd[b + f"{a}.norm_k.weight"] = (1 + 0.1 * torch.randn(D, generator=g)).to(dtype)
-        sd[b + "norm3.weight"] = (1 + 0.1 * torch.randn(D, generator=g)).to(dtype)
-        sd[b + "norm3.bias"] = (0.05 * torch.randn(D, generator=g)).to(dtype)
+            sd[b + f"{a}.norm_q.weight"] = (1 + 0.1 * _R.randn(D)).to(dtype)
+            sd[b + f"{a}.norm_k.weight"] = (1 + 0.1 * _R.randn(D)).to(dtype)
+        sd[b + "norm3.weight"] = (1 + 0.1 * _R.randn(D)).to(dtype)
+        sd[b + "norm3.bias"] = (0.05 * _R.randn(D)).to(dtype)
         lin(b + "ffn.0", cfg.ffn_dim, D); lin(b + "ffn.2", D, cfg.ffn_dim)
-        sd[b + "modulation"] = (torch.randn(1, 6, D, generator=g) / D ** 0.5).to(dtype)
+        sd[b + "modulation"] = (_R.randn(1, 6, D) / D ** 0.5).to(dtype)
     lin("head.head", cfg.out_dim * math.prod(cfg.patch_size), D)
-    sd["head.modulation"] = (torch.randn(1, 2, D, generator=g) / D ** 0.5).to(dtype)
+    sd["head.modulation"] = (_R.randn(1, 2, D) / D ** 0.5).to(dtype)
     return sd
 
 
 def sinusoidal_embedding_1d(dim: int, position: torch.Tensor) -> torch.Tensor:
     half = dim // 2
     position = position.to(torch.float64)
-    sinusoid = torch.outer(position, torch.pow(10000, -torch.arange(half, dtype=torch.float64) / half))
+    sinusoid = torch.outer(position, torch.pow(10000, -torch.arange(half, dtype=torch.float64, device=position.device) / half))
     return torch.cat([torch.cos(sinusoid), torch.sin(sinusoid)], dim=1)
 
 
-def rope_tables(cfg: WanConfig, F_: int, H: int, W: int):
+def rope_tables(cfg: WanConfig, F_: int, H: int, W: int, device=None):
     """(cos, sin) [F*H*W, head_dim] fp32, repeat-interleaved over the complex pairs (rope_params + rope_apply)."""
     d = cfg.head_dim
     dims = [d - 4 * (d // 6), 2 * (d // 6), 2 * (d // 6)]
 
     def ang(n, dim):
-        return torch.outer(torch.arange(n, dtype=torch.float64),
-                           1.0 / torch.pow(10000, torch.arange(0, dim, 2, dtype=torch.float64) / dim))
+        return torch.outer(torch.arange(n, dtype=torch.float64, device=device),
+                           1.0 / torch.pow(10000, torch.arange(0, dim, 2, dtype=torch.float64, device=device) / dim))
 
     at, ah, aw = ang(F_, dims[0]), ang(H, dims[1]), ang(W, dims[2])
     a = torch.cat([at[:, None, None, :].expand(F_, H, W, -1), ah[None, :, None, :].expand(F_, H, W, -1),
@@ -110,7 +117,8 @@ def layer_norm(x, eps, w=None, b=None):
 
 def attention(q, k, v):
     """q [Sq, n, d], k/v [Skv, n, d] -> [Sq, n*d]"""
-    o = F.scaled_dot_product_attention(q.transpose(0, 1)[None], k.transpose(0, 1)[None], v.transpose(0, 1)[None])[0]
+    from .dit_torch import sdpa                      # explicit fp32 softmax for fp32 CUDA inputs, F.sdpa otherwise
+    o = sdpa(q.transpose(0, 1)[None], k.transpose(0, 1)[None], v.transpose(0, 1)[None])[0]
     return o.transpose(0, 1).flatten(1)
 
 
@@ -144,7 +152,7 @@ def model_forward(sd, cfg: WanConfig, x, t, context, num_layers: int | None = No
     S = f * h * w
     tok = F.conv3d(x[None], sd["patch_embedding.weight"], sd["patch_embedding.bias"], stride=cfg.patch_size)[0]   # [D, f, h, w]
     xs = tok.flatten(1).transpose(0, 1)                                                                           # [S, D]
-    t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+    t = torch.as_tensor(t, dtype=torch.float32, device=x.device).reshape(-1)
     if t.numel() == 1:
         t = t.expand(S)
     emb = sinusoidal_embedding_1d(cfg.freq_dim, t).float()
@@ -154,7 +162,7 @@ def model_forward(sd, cfg: WanConfig, x, t, context, num_layers: int | None = No
     ctx = torch.cat([context, context.new_zeros(cfg.text_len - context.shape[0], context.shape[1])])
     ctx = F.linear(F.gelu(F.linear(ctx, sd["text_embedding.0.weight"], sd["text_embedding.0.bias"]), approximate="tanh"),
                    sd["text_embedding.2.weight"], sd["text_embedding.2.bias"])
-    cos, sin = rope_tables(cfg, f, h, w)
+    cos, sin = rope_tables(cfg, f, h, w, device=x.device)
     L = cfg.num_layers if num_layers is None else num_layers
     for i in range(L):
         xs = block_forward(sd, cfg, i, xs, e0, ctx, cos, sin)
