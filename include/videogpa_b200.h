@@ -47,8 +47,12 @@ enum {
   VGPA_EPI_GATE_RES = 2,  /* out = out + gate[b, seg(row)] * (acc + bias)   (adaLN-zero residual)  */
   VGPA_EPI_QKV = 3,       /* fused to_q|to_k|to_v: per-head LayerNorm(64) on q,k + 3-D RoPE on     */
                           /* video rows; v passes through      (CogVideoXAttnProcessor2_0)         */
-  VGPA_EPI_ACCUM = 4      /* out = bf16(out + alpha * acc), one rounding (PEFT LoRA merge,         */
+  VGPA_EPI_ACCUM = 4,     /* out = bf16(out + alpha * acc), one rounding (PEFT LoRA merge,         */
                           /* generate/CogVideoX-5B.py:29-30: W <- W + (lora_alpha/r) * B @ A)      */
+  VGPA_EPI_GATE_RES_F32 = 5 /* fp32 residual stream: out is float [M, ldo];                        */
+                          /* out = out + gate[b, seg(row)] * bf16(acc + bias) in fp32 (WanModel    */
+                          /* under torch.autocast(bf16): bf16 linear output added to an fp32 x,    */
+                          /* generate/Wan2.2-TI2V-5B.py:120-129)                                   */
 };
 
 typedef struct vgpa_linear_args {
@@ -158,6 +162,10 @@ typedef struct vgpa_layernorm_args {
   const void* shift_vid;
   const void* scale_vid;
   int64_t mod_stride_b;
+  /* 1: x is float [rows, ldx] (fp32 residual stream of the Wan2.2 forward); the normalisation, affine and modulation are
+   * then evaluated in fp32 and rounded to bf16 once (torch.autocast semantics) instead of torch's eager-bf16 rounding
+   * after every op. 0: x is bf16. */
+  int32_t x_is_f32;
 } vgpa_layernorm_args;
 
 int vgpa_layernorm_modulate_bf16(const vgpa_layernorm_args* args, void* stream);

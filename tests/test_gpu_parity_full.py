@@ -60,9 +60,10 @@ def test_cogvideox_5b_forward_42_layers_full_size(lib, fp32_strict):
     e, eb = errs(out, ref), errs(eager, ref)
     print(f"\n42-layer forward vs fp32 oracle: ours {e}  |  oracle in eager bf16 {eb}")
     # 84 residual updates of bf16 rounding: ~1e-2 relative for either bf16 path; a swapped shift / scale / gate gives > 0.3
-    assert e["rel_l2"] < max(2.5e-2, 1.5 * eb["rel_l2"]), (e, eb)
-    assert e["cos"] > 0.9995, e
-    assert e["max_rel"] < max(5e-2, 2.0 * eb["max_rel"]), (e, eb)
+    # measured: ours rel_l2 1.74e-2 / cos 0.99985 / max_rel 1.98e-2; eager bf16 1.76e-2 / 0.99985 / 1.92e-2
+    assert e["rel_l2"] < min(2.5e-2, 1.3 * eb["rel_l2"]), (e, eb)
+    assert e["cos"] > 0.9997, e
+    assert e["max_rel"] < min(4e-2, 1.6 * eb["max_rel"]), (e, eb)
 
 
 def test_ddim_50_steps_latent_drift(lib, fp32_strict):
@@ -101,7 +102,8 @@ def test_ddim_50_steps_latent_drift(lib, fp32_strict):
     assert torch.isfinite(lat.float()).all()
     # the latent is re-rounded to bf16 every step (as in the reference's bf16 pipeline) and the error of 100 forwards
     # feeds back through the guidance (x6): the loop stays within a few percent of the fp32 trajectory
-    assert e["rel_l2"] < 6e-2 and e["cos"] > 0.998, e
+    # measured: rel_l2 2.8e-2, cos 0.9996, max_rel 3.0e-2
+    assert e["rel_l2"] < 4e-2 and e["cos"] > 0.999 and e["max_rel"] < 6e-2, e
 
 
 def test_vae_decode_full_size_tiled(lib, fp32_strict):
@@ -122,9 +124,10 @@ def test_vae_decode_full_size_tiled(lib, fp32_strict):
     assert out.shape == ref.shape == (1, 3, 49, 480, 720) and torch.isfinite(out.float()).all()
     e, eb = errs(out, ref), errs(eager, ref)
     print(f"\nfull-size tiled VAE decode vs fp32 oracle: ours {e}  |  oracle in eager bf16 {eb}")
-    assert e["rel_l2"] < max(3e-2, 1.5 * eb["rel_l2"]), (e, eb)
-    assert e["cos"] > 0.999, e
-    assert e["max_rel"] < max(8e-2, 2.0 * eb["max_rel"]), (e, eb)
+    # measured: ours rel_l2 1.57e-2 / cos 0.99988 / max_rel 1.9e-2; eager bf16 1.78e-2 / 0.99984 / 2.1e-2
+    assert e["rel_l2"] < min(2.5e-2, 1.3 * eb["rel_l2"]), (e, eb)
+    assert e["cos"] > 0.9997, e
+    assert e["max_rel"] < min(4e-2, 1.6 * eb["max_rel"]), (e, eb)
 
 
 def test_wan_ti2v_5b_forward_full_size(lib, fp32_strict):
@@ -132,9 +135,9 @@ def test_wan_ti2v_5b_forward_full_size(lib, fp32_strict):
     1280x704 latent [48, 21, 44, 80] (S = 18 480), per-token timesteps with the first frame at t = 0
     (generate/Wan2.2-TI2V-5B.py:120-129; train/Wan2.2-TI2V-5B/03_train.py:119-125), against the fp32 oracle on the GPU.
 
-    The Wan repository runs this forward under torch.autocast(bf16) with an fp32 residual stream; videogpa_b200.wan keeps the
-    residual stream in bf16 (declared deviation). The same oracle under autocast gives the error of the reference's own
-    precision plan; ours must stay within 1.5x of it — that is the proof that the deviation is inside bf16 noise."""
+    The Wan repository runs this forward under torch.autocast(bf16) with an fp32 residual stream, and so does
+    videogpa_b200.wan (round 1 kept the stream in bf16 and measured 1.5e-2 here, 2.9x the autocast error). The same oracle
+    under autocast gives the error of the reference's own precision plan; ours must stay within 1.5x of it."""
     from oracle import wan_torch as WO
     from videogpa_b200.wan import WanConfig, WanTransformer3D
     ocfg = WO.WanConfig()
@@ -153,6 +156,6 @@ def test_wan_ti2v_5b_forward_full_size(lib, fp32_strict):
     assert out.shape == ref.shape == (48, 21, 44, 80) and torch.isfinite(out.float()).all()
     e, ea = errs(out, ref), errs(auto, ref)
     print(f"\nWan2.2 TI2V-5B forward (S = 18 480) vs fp32 oracle: ours {e}  |  oracle under autocast(bf16), fp32 residual {ea}")
-    assert e["rel_l2"] < max(3e-2, 1.5 * ea["rel_l2"]), (e, ea)
-    assert e["cos"] > 0.999, e
-    assert e["max_rel"] < max(8e-2, 2.0 * ea["max_rel"]), (e, ea)
+    assert e["rel_l2"] < max(6e-3, 1.5 * ea["rel_l2"]), (e, ea)
+    assert e["cos"] > 0.9999, e
+    assert e["max_rel"] < max(1.5e-2, 2.0 * ea["max_rel"]), (e, ea)

@@ -158,3 +158,39 @@ def test_wan_generate_cli_synthetic(lib, tmp_path, capsys):
     assert not (out / "s2").exists() and not (out / "s3").exists()
     g.main(argv)
     assert "Skip existing: s1" in capsys.readouterr().out
+
+
+def test_fp32_residual_kernels_vs_torch(lib):
+    """The two kernels behind the fp32 residual stream of the Wan2.2 forward (torch.autocast semantics): LayerNorm + modulation
+    on a float32 row, one bf16 rounding; gated residual update out_f32 += gate * bf16(acc + bias)."""
+    from videogpa_b200 import dense
+    g = torch.Generator(device="cuda").manual_seed(7)
+    S, D, hw = 300, 3072, 40
+    x = torch.randn(S, D, generator=g, device="cuda") * 3 + 0.5
+    shift = [(torch.randn(1, D, generator=g, device="cuda") * 0.2).to(BF) for _ in range(2)]
+    scale = [(torch.randn(1, D, generator=g, device="cuda") * 0.2).to(BF) for _ in range(2)]
+    n = dense.layernorm_modulate(x, None, None, eps=1e-6, rows_per_sample=S, text_rows=hw, shift_txt=shift[0], scale_txt=scale[0],
+                                 shift_vid=shift[1], scale_vid=scale[1], mod_stride_b=0)
+    ln = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
+    is_first = (torch.arange(S, device="cuda") < hw)[:, None]
+    ref = ln * (1 + torch.where(is_first, scale[0].float(), scale[1].float())) + torch.where(is_first, shift[0].float(), shift[1].float())
+    assert n.dtype == BF and relmax(n, ref) < 5e-3                                    # one bf16 rounding
+    w, b = (1 + 0.1 * torch.randn(D, generator=g, device="cuda")).to(BF), (0.1 * torch.randn(D, generator=g, device="cuda")).to(BF)
+    n2 = dense.layernorm_modulate(x, w, b, eps=1e-6)
+    assert relmax(n2, torch.nn.functional.layer_norm(x, (D,), w.float(), b.float(), 1e-6)) < 5e-3
+    # gated residual on the fp32 stream
+    a = (torch.randn(S, 512, generator=g, device="cuda") * 0.5).to(BF)
+    wt = (torch.randn(D, 512, generator=g, device="cuda") * 0.05).to(BF)
+    bias = (torch.randn(D, generator=g, device="cuda") * 0.1).to(BF)
+    gate = [(torch.randn(1, D, generator=g, device="cuda")).to(BF) for _ in range(2)]
+    out = x.clone()
+    dense.linear(a, wt, bias, out=out, epilogue=dense.EPI_GATE_RES_F32, rows_per_sample=S, text_rows=hw, gate_txt=gate[0], gate_vid=gate[1],
+                 gate_stride_b=0)
+    y = (a.float() @ wt.float().t() + bias.float()).to(BF).float()
+    want = x + torch.where(is_first, gate[0].float(), gate[1].float()) * y
+    assert out.dtype == torch.float32 and (out - want).abs().max().item() < 2e-2 * y.abs().max().item()   # y differs by <= 1 bf16 ulp
+    out2 = x.clone()
+    dense.linear(a, wt, bias, out=out2, epilogue=dense.EPI_GATE_RES_F32)                                   # no gate = 1
+    assert (out2 - (x + y)).abs().max().item() < 2e-2 * y.abs().max().item()
+    with pytest.raises(RuntimeError):
+        dense.linear(a, wt, bias, out=x.to(BF), epilogue=dense.EPI_GATE_RES_F32)                           # the stream must be float32

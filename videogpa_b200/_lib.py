@@ -71,6 +71,7 @@ class LayerNormArgs(C.Structure):
         ("rows_per_sample", c_i32), ("text_rows", c_i32),
         ("shift_txt", c_void_p), ("scale_txt", c_void_p), ("shift_vid", c_void_p), ("scale_vid", c_void_p),
         ("mod_stride_b", c_i64),
+        ("x_is_f32", c_i32),
     ]
 
 
@@ -124,7 +125,7 @@ class ComposeArgs(C.Structure):
     ]
 
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV, EPI_ACCUM = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV, EPI_ACCUM, EPI_GATE_RES_F32 = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_SILU = 0, 1
 SCHED_DDIM, SCHED_DPM = 0, 1
 

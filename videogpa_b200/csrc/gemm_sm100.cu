@@ -105,6 +105,29 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
         }
       }
     }
+  } else if constexpr (EPI == VGPA_EPI_GATE_RES_F32) {
+    // fp32 residual stream: x <- x + gate * bf16(y), evaluated and stored in fp32 (no bf16 store below)
+    int srow = row, b = 0;
+    if (ep.rows_per_sample > 0) { b = row / ep.rows_per_sample; srow = row - b * ep.rows_per_sample; }
+    const __nv_bfloat16* g = (srow < ep.text_rows ? ep.gate_txt : ep.gate_vid);
+    if (live) {
+      float4* xo = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col0);
+      const uint2* gp = (g != nullptr) ? reinterpret_cast<const uint2*>(g + b * ep.gate_stride_b + col0) : nullptr;
+      float4 r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = xo[i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float2 g0 = make_float2(1.f, 1.f), g1 = g0;
+        if (gp != nullptr) { const uint2 gg = __ldg(gp + i); g0 = unpack_bf16x2(gg.x); g1 = unpack_bf16x2(gg.y); }
+        r[i].x += g0.x * bf16_round(v[4 * i + 0]);
+        r[i].y += g0.y * bf16_round(v[4 * i + 1]);
+        r[i].z += g1.x * bf16_round(v[4 * i + 2]);
+        r[i].w += g1.y * bf16_round(v[4 * i + 3]);
+        xo[i] = r[i];
+      }
+    }
+    return;
   } else if constexpr (EPI == VGPA_EPI_ACCUM) {
     // out <- bf16(out + alpha * acc): one rounding (PEFT merge `weight += scaling * B @ A`)
     if (live) {
@@ -425,7 +448,7 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
     VGPA_CHECK(a->ln_q_w && a->ln_q_b && a->ln_k_w && a->ln_k_b, "vgpa_linear_bf16: QKV epilogue needs q/k LayerNorm params");
     VGPA_CHECK((a->rope_cos == nullptr) == (a->rope_sin == nullptr), "vgpa_linear_bf16: rope cos/sin must both be set or both null");
   }
-  if (a->epilogue == VGPA_EPI_GATE_RES) {
+  if (a->epilogue == VGPA_EPI_GATE_RES || a->epilogue == VGPA_EPI_GATE_RES_F32) {
     VGPA_CHECK((a->gate_txt == nullptr) == (a->gate_vid == nullptr), "vgpa_linear_bf16: gate_txt/gate_vid must both be set or both null");
   }
 
@@ -454,6 +477,7 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
     VGPA_GEMM_DISPATCH(VGPA_EPI_GATE_RES)
     VGPA_GEMM_DISPATCH(VGPA_EPI_QKV)
     VGPA_GEMM_DISPATCH(VGPA_EPI_ACCUM)
+    VGPA_GEMM_DISPATCH(VGPA_EPI_GATE_RES_F32)
     default:
       break;
   }

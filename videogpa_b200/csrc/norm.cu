@@ -14,7 +14,7 @@ namespace {
 constexpr int LN_WARPS = 8;
 
 struct LnParams {
-  const __nv_bfloat16* x;
+  const void* x;        // bf16, or float when XF32
   __nv_bfloat16* out;
   long long ldx, ldo;
   int rows, D;
@@ -30,20 +30,32 @@ struct LnParams {
 };
 
 // VPL = uint4 vectors per lane (D = VPL * 256)
-template <int VPL>
+// XF32: x is the fp32 residual stream of the Wan2.2 forward; everything up to the single bf16 rounding of the output is fp32
+// (torch.autocast semantics). Otherwise x is bf16 and the modulation follows torch's eager-bf16 roundings.
+template <int VPL, bool XF32>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_modulate_kernel(LnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= p.rows) return;
-  const uint4* xr = reinterpret_cast<const uint4*>(p.x + static_cast<long long>(row) * p.ldx);
   float v[VPL * 8];
+  if constexpr (XF32) {
+    const float4* xr = reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + static_cast<long long>(row) * p.ldx);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const uint4 u = xr[i * 32 + lane];
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    v[i * 8 + 0] = a.x; v[i * 8 + 1] = a.y; v[i * 8 + 2] = b.x; v[i * 8 + 3] = b.y;
-    v[i * 8 + 4] = c.x; v[i * 8 + 5] = c.y; v[i * 8 + 6] = d.x; v[i * 8 + 7] = d.y;
+    for (int i = 0; i < VPL; ++i) {
+      const float4 a = xr[(i * 32 + lane) * 2], b = xr[(i * 32 + lane) * 2 + 1];
+      v[i * 8 + 0] = a.x; v[i * 8 + 1] = a.y; v[i * 8 + 2] = a.z; v[i * 8 + 3] = a.w;
+      v[i * 8 + 4] = b.x; v[i * 8 + 5] = b.y; v[i * 8 + 6] = b.z; v[i * 8 + 7] = b.w;
+    }
+  } else {
+    const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.x) + static_cast<long long>(row) * p.ldx);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const uint4 u = xr[i * 32 + lane];
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      v[i * 8 + 0] = a.x; v[i * 8 + 1] = a.y; v[i * 8 + 2] = b.x; v[i * 8 + 3] = b.y;
+      v[i * 8 + 4] = c.x; v[i * 8 + 5] = c.y; v[i * 8 + 6] = d.x; v[i * 8 + 7] = d.y;
+    }
   }
   float s = 0.f;
 #pragma unroll
@@ -81,6 +93,24 @@ ln_modulate_kernel(LnParams p) {
       const uint32_t bv[4] = {bu.x, bu.y, bu.z, bu.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16x2(bv[k]); y[2 * k] += f.x; y[2 * k + 1] += f.y; }
+    }
+    if constexpr (XF32) {
+      if (sc4) {
+        const uint4 su = __ldg(sc4 + idx);
+        const uint32_t sv[4] = {su.x, su.y, su.z, su.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16x2(sv[k]); y[2 * k] *= 1.0f + f.x; y[2 * k + 1] *= 1.0f + f.y; }
+      }
+      if (sh4) {
+        const uint4 su = __ldg(sh4 + idx);
+        const uint32_t sv[4] = {su.x, su.y, su.z, su.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16x2(sv[k]); y[2 * k] += f.x; y[2 * k + 1] += f.y; }
+      }
+      uint4 o;
+      o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]); o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+      orow[idx] = o;
+      continue;
     }
     // eager bf16 semantics with packed bf16x2 hardware ops (one rounding per op, exactly what torch's bf16 kernels do):
     // n = bf16(LN(x));  n = n * bf16(1 + scale);  n = n + shift
@@ -120,7 +150,7 @@ extern "C" int vgpa_layernorm_modulate_bf16(const vgpa_layernorm_args* a, void* 
   VGPA_CHECK((a->shift_txt == nullptr) == (a->shift_vid == nullptr) && (a->scale_txt == nullptr) == (a->scale_vid == nullptr),
              "vgpa_layernorm_modulate_bf16: text/video modulation pointers must be set together");
   LnParams p;
-  p.x = static_cast<const __nv_bfloat16*>(a->x);
+  p.x = a->x;
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.ldx = a->ldx; p.ldo = a->ldo; p.rows = a->rows; p.D = a->D;
   p.w = static_cast<const __nv_bfloat16*>(a->ln_weight);
@@ -135,7 +165,11 @@ extern "C" int vgpa_layernorm_modulate_bf16(const vgpa_layernorm_args* a, void* 
   const int grid = (a->rows + LN_WARPS - 1) / LN_WARPS;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (a->D / 256) {
-#define VGPA_LN_CASE(V) case V: ln_modulate_kernel<V><<<grid, LN_WARPS * 32, 0, s>>>(p); break;
+#define VGPA_LN_CASE(V)                                                              \
+  case V:                                                                          \
+    if (a->x_is_f32) ln_modulate_kernel<V, true><<<grid, LN_WARPS * 32, 0, s>>>(p);  \
+    else ln_modulate_kernel<V, false><<<grid, LN_WARPS * 32, 0, s>>>(p);             \
+    break;
     VGPA_LN_CASE(1) VGPA_LN_CASE(2) VGPA_LN_CASE(3) VGPA_LN_CASE(4) VGPA_LN_CASE(5) VGPA_LN_CASE(6)
     VGPA_LN_CASE(7) VGPA_LN_CASE(8) VGPA_LN_CASE(9) VGPA_LN_CASE(10) VGPA_LN_CASE(11) VGPA_LN_CASE(12)
     VGPA_LN_CASE(13) VGPA_LN_CASE(14) VGPA_LN_CASE(15) VGPA_LN_CASE(16)

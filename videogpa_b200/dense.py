@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttentionBwdArgs, ACT_NONE, ACT_SILU, EPI_ACCUM, EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV,
+from ._lib import (AttentionBwdArgs, ACT_NONE, ACT_SILU, EPI_ACCUM, EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RES, EPI_GATE_RES_F32, EPI_QKV,
                    SCHED_DDIM, SCHED_DPM, AttentionArgs, LayerNormArgs, LinearArgs, SchedArgs)
 
 BF16 = torch.bfloat16
@@ -53,10 +53,10 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *
     if K != K2:
         raise RuntimeError(f"linear: K mismatch {K} vs {K2}")
     if out is None:
-        if epilogue in (EPI_GATE_RES, EPI_ACCUM):
+        if epilogue in (EPI_GATE_RES, EPI_ACCUM, EPI_GATE_RES_F32):
             raise RuntimeError("linear: this epilogue updates `out` in place; pass the tensor to update")
         out = torch.empty((M, N), dtype=BF16, device=a.device)
-    _rows(_req(out, BF16, "out", contiguous=False), "out")
+    _rows(_req(out, torch.float32 if epilogue == EPI_GATE_RES_F32 else BF16, "out", contiguous=False), "out")
     if out.shape[0] != M or out.shape[1] != N:
         raise RuntimeError(f"linear: out shape {tuple(out.shape)} != ({M}, {N})")
     args = LinearArgs()
@@ -181,7 +181,8 @@ def layernorm_modulate(x: torch.Tensor, ln_weight: torch.Tensor | None, ln_bias:
                        mod_stride_b: int = 0) -> torch.Tensor:
     """LN(x) * (1 + scale[b, seg]) + shift[b, seg] over [rows, D]; see vgpa_layernorm_modulate_bf16."""
     lib = _lib.load()
-    _rows(_req(x, BF16, "x", contiguous=False), "x")
+    x_f32 = x.dtype == torch.float32                     # fp32 residual stream (Wan2.2): fp32 math, one bf16 rounding
+    _rows(_req(x, torch.float32 if x_f32 else BF16, "x", contiguous=False), "x")
     rows, D = x.shape
     if out is None:
         out = torch.empty((rows, D), dtype=BF16, device=x.device)
@@ -193,6 +194,7 @@ def layernorm_modulate(x: torch.Tensor, ln_weight: torch.Tensor | None, ln_bias:
     a.shift_txt, a.scale_txt, a.shift_vid, a.scale_vid = (_lib.ptr(shift_txt), _lib.ptr(scale_txt),
                                                         _lib.ptr(shift_vid), _lib.ptr(scale_vid))
     a.mod_stride_b = mod_stride_b
+    a.x_is_f32 = 1 if x_f32 else 0
     _lib.check(lib.vgpa_layernorm_modulate_bf16(C.byref(a), _lib.current_stream()), "vgpa_layernorm_modulate_bf16")
     return out
 

@@ -12,8 +12,11 @@ Per-token timesteps (Wan2.2 TI2V: the first latent frame is the conditioning ima
 train/Wan2.2-TI2V-5B/03_train.py:119-125) take only two values, so modulation is computed for two row segments
 (first-frame tokens | the rest) and selected per row inside the kernels.
 
-Known deviation (parity unpinned anyway, see oracle/wan_torch.py): the residual stream is bf16 here; the Wan repo keeps
-it in fp32 under autocast.
+Precision plan = the Wan repo's (torch.autocast(bf16) around an fp32 model input): the residual stream x is fp32, every
+linear consumes and produces bf16 with fp32 accumulation, LayerNorm + modulation are evaluated in fp32 on the fp32 stream
+and rounded to bf16 once for the next linear, and the gated residual updates add in fp32 (vgpa_linear_bf16 with
+VGPA_EPI_GATE_RES_F32, vgpa_layernorm_modulate_bf16 with x_is_f32). tests/test_gpu_parity_full.py measures the full-size
+forward against the fp32 oracle next to the same oracle under autocast.
 """
 from __future__ import annotations
 
@@ -211,7 +214,7 @@ class WanTransformer3D:
         hw = h * w_
         S = F_ * hw
         frames = lat.to(device=dev, dtype=BF16).permute(1, 0, 2, 3).contiguous()                      # [F, C, H, W]
-        x = dense.linear(dense.patchify(frames), self.patch_w, self.patch_b)                           # [S, D]
+        x = dense.linear(dense.patchify(frames), self.patch_w, self.patch_b).float()                   # [S, D] fp32 residual stream
         # time embedding for the two distinct timesteps: row 0 = first-frame tokens, row 1 = the rest
         ts = torch.tensor([t_first, t_rest], dtype=torch.float32, device=dev)
         sin_emb = dense.timestep_embedding(ts, c.freq_dim)
@@ -224,7 +227,7 @@ class WanTransformer3D:
         ctx = dense.linear(dense.linear(ctx_in, self.te0_w, self.te0_b, epilogue=dense.EPI_BIAS_GELU), self.te2_w, self.te2_b)
         rope = rope_tables(c, F_, h, w_, device=dev)
 
-        n = torch.empty_like(x)
+        n = torch.empty((S, D), dtype=BF16, device=dev)
         qkv = torch.empty((S, 3 * D), dtype=BF16, device=dev)
         att = torch.empty((1, S, D), dtype=BF16, device=dev)
         qc = torch.empty((S, D), dtype=BF16, device=dev)
@@ -242,7 +245,7 @@ class WanTransformer3D:
             _rmsnorm_rope(qkv[:, D:2 * D], blk.nk, c.eps, rope, hd)
             q3 = qkv.view(1, S, 3 * D)
             dense.attention(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], n_heads, out=att, head_dim=hd)
-            dense.linear(att.view(S, D), blk.w_o, blk.b_o, out=x, epilogue=dense.EPI_GATE_RES, **seg,
+            dense.linear(att.view(S, D), blk.w_o, blk.b_o, out=x, epilogue=dense.EPI_GATE_RES_F32, **seg,
                          gate_txt=mod(2, 0), gate_vid=mod(2, 1), gate_stride_b=0)
             # cross-attention over the embedded text
             dense.layernorm_modulate(x, blk.n3_w, blk.n3_b, eps=c.eps, out=n)
@@ -252,12 +255,12 @@ class WanTransformer3D:
             _rmsnorm_rope(kvc[:, :D], blk.cnk, c.eps)
             k3 = kvc.view(1, c.text_len, 2 * D)
             dense.attention(qc.view(1, S, D), k3[..., :D], k3[..., D:], n_heads, out=att, head_dim=hd)
-            dense.linear(att.view(S, D), blk.w_co, blk.b_co, out=x, epilogue=dense.EPI_GATE_RES)
+            dense.linear(att.view(S, D), blk.w_co, blk.b_co, out=x, epilogue=dense.EPI_GATE_RES_F32)
             # feed-forward
             dense.layernorm_modulate(x, None, None, eps=c.eps, out=n, **seg, shift_txt=mod(3, 0), scale_txt=mod(4, 0),
                                      shift_vid=mod(3, 1), scale_vid=mod(4, 1), mod_stride_b=0)
             dense.linear(n, blk.w_f0, blk.b_f0, out=ffh, epilogue=dense.EPI_BIAS_GELU)
-            dense.linear(ffh, blk.w_f2, blk.b_f2, out=x, epilogue=dense.EPI_GATE_RES, **seg,
+            dense.linear(ffh, blk.w_f2, blk.b_f2, out=x, epilogue=dense.EPI_GATE_RES_F32, **seg,
                          gate_txt=mod(5, 0), gate_vid=mod(5, 1), gate_stride_b=0)
         # head: LN (1 + e1) + e0 with e = head.modulation + time embedding (before the projection)
         hm = _add_rows(torch.cat([e, e], dim=1), self.head_mod)                                        # [2, 2D]
