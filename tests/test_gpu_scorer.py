@@ -25,7 +25,9 @@ def test_mvcs_golden_and_oracle(lib, golden, name):
     score = MVCSMetric(device="cuda").compute(gt=None, rep=None, depths=cuda(d), intrinsics=cuda(K), extrinsics=cuda(E))
     assert isinstance(score, float)
     assert abs(score - float(g[name + "_score"])) <= 1e-6           # vs the reference file's own output
-    assert abs(score - o.mvcs(d, K, E)) <= 1e-9                      # vs the oracle (same op order)
+    # vs the oracle: the mask is bit-exact (next test); the sampled values come from the merged-matrix FMA evaluation and
+    # differ from the reference's fp32 operation order by a few ulp per pixel (mvcs.cu header)
+    assert abs(score - o.mvcs(d, K, E)) <= 1e-6
 
 
 @pytest.mark.parametrize("name", ["kat", "yaw_4x4", "big_motion_k4", "empty_pair"])
@@ -36,8 +38,9 @@ def test_mvcs_mask_counts_bit_exact(lib, golden, name):
     K, E = g[name + "_K"], g[name + "_E"]
     _, mse_ref, cnt_ref = o.mvcs(d, K, E, return_pairs=True)
     scores, mse, cnt = mvcs_batch(cuda(d)[None], cuda(K)[None], cuda(E)[None], return_pairs=True)
-    assert np.array_equal(cnt.cpu().numpy()[0], cnt_ref)             # mask sizes: exact
-    np.testing.assert_allclose(mse.cpu().numpy()[0], mse_ref, rtol=1e-10, atol=1e-14)   # fp64 sums of identical fp32 terms
+    assert np.array_equal(cnt.cpu().numpy()[0], cnt_ref)             # mask sizes (integer work): exact
+    # per-pair MSE (floating point): same pixels, values within a few fp32 ulp of the reference's operation order
+    np.testing.assert_allclose(mse.cpu().numpy()[0], mse_ref, rtol=2e-5, atol=1e-12)
 
 
 def test_mvcs_batched_equals_single_and_production_size(lib):
@@ -57,7 +60,8 @@ def test_mvcs_batched_equals_single_and_production_size(lib):
         s1 = mvcs_batch(cuda(depth[n:n + 1]), cuda(K[n:n + 1]), cuda(E[n:n + 1])).cpu().numpy()[0]
         assert abs(s1 - scores[n]) < 1e-12                           # batching does not change a clip's score
     s_ref, mse_ref, cnt_ref = o.mvcs(depth[0], K[0], E[0], return_pairs=True)
-    assert np.array_equal(cnt.cpu().numpy()[0], cnt_ref) and abs(scores[0] - s_ref) < 1e-9
+    assert np.array_equal(cnt.cpu().numpy()[0], cnt_ref) and abs(scores[0] - s_ref) < 1e-6
+    print("production-size per-pair MSE max rel diff vs oracle:", float(np.max(np.abs(mse.cpu().numpy()[0] - mse_ref) / mse_ref)))
     # size-independent property: identical cameras and depth-consistent frames -> error 0 -> score 1
     flat = np.full((1, 4, 64, 64), 3.0, dtype=np.float32)
     I = np.tile(np.eye(4, dtype=np.float32)[:3], (1, 4, 1, 1))
@@ -288,7 +292,7 @@ def test_video_processor_da3_path_vs_oracle_composition(lib):
         assert abs(res[th]["MSE"] - want_mse) <= 1e-5 * max(1.0, want_mse)
         assert abs(res[th]["Consistency_Score"] - (want_mse + want_lp)) <= 2e-5 * max(1.0, want_mse + want_lp)
         assert abs(res[th]["motion_norm"] - o.motion_score(preds["extrinsic"])) <= 1e-6
-        assert abs(res[th]["MVCS"] - o.mvcs(preds["depth"], preds["intrinsic"], preds["extrinsic"])) <= 1e-9
+        assert abs(res[th]["MVCS"] - o.mvcs(preds["depth"], preds["intrinsic"], preds["extrinsic"])) <= 1e-6
     assert res[0]["MVCS"] == res[40]["MVCS"]                                                # MVCS ignores the threshold
     # additive batched API: one launch for many clips, result stays on the device
     d = torch.from_numpy(preds["depth"]).cuda()[None].repeat(3, 1, 1, 1)

@@ -151,6 +151,20 @@ if rank == 0:
     ps[2].grad = torch.ones(2, 2)
 assert average_gradients(ps, bucket_bytes=64) == 2          # 12 + 5 floats exceed 64 bytes -> [p0], [p1, p2]
 assert torch.all(ps[0].grad == 1.5) and torch.equal(ps[1].grad, torch.arange(5.0) * 1.5) and torch.all(ps[2].grad == 0.5)
+# the overlapped reducer: same averages as average_gradients, launched from autograd hooks, silent while not armed
+from videogpa_b200.parallel import BucketedGradReducer
+qs = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2))]
+red = BucketedGradReducer(qs, bucket_bytes=64)
+assert [sorted(b) for b in red.buckets] == [[1, 2], [0]]       # reverse (backward) order, 64-byte buckets
+red.armed = False
+((qs[0].sum() + qs[1].sum()) * float(rank + 1)).backward()     # accumulation micro-batch: no collective
+assert not red._inflight
+red.armed = True
+((qs[0].sum() + qs[1].sum()) * float(rank + 1)).backward()     # q2 gets no gradient at all
+st = red.finish()
+assert st["buckets"] == 2 and st["bytes"] == (12 + 5 + 4) * 4
+assert torch.all(qs[0].grad == 3.0) and torch.all(qs[1].grad == 3.0) and torch.all(qs[2].grad == 0.0)   # mean over ranks of 2 x (rank + 1)
+red.remove()
 dist.barrier(); dist.destroy_process_group()
 print("worker ok", rank)
 '''

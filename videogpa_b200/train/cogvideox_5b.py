@@ -67,7 +67,7 @@ def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int 
     `checkpoint_every_n_steps` optimizer steps (ModelCheckpoint(every_n_train_steps=...), :267-274)."""
     import time
     import torch.distributed as dist
-    from ..parallel import average_gradients
+    from ..parallel import BucketedGradReducer
     opt = step.configure_optimizers(lr=config["learning_rate"])
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: cosine_schedule_with_warmup(s, config.get("warmup_steps", 500), config["max_steps"]))
     params = step.trainable.parameters()
@@ -75,14 +75,16 @@ def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int 
     max_steps = int(config["max_steps"])
     ckpt_every = int(config.get("checkpoint_every_n_steps", 0) or 0)
     ddp = dist.is_available() and dist.is_initialized()
+    # DDP: bucketed all-reduce of the LoRA gradients, launched from autograd hooks while backward is still running
+    reducer = BucketedGradReducer(params, bucket_bytes=int(config.get("ddp_bucket_bytes", 32 << 20))) if ddp else None
     gstep, last, val_hist, epoch = 0, float("nan"), [], 0
     t_start, world = time.time(), (dist.get_world_size() if ddp else 1)
     opt.zero_grad(set_to_none=True)
 
     def optimizer_step():
         nonlocal gstep
-        if ddp:
-            average_gradients(params)
+        if reducer is not None:
+            reducer.finish()
         if clip:
             torch.nn.utils.clip_grad_norm_(params, float(clip))
         opt.step()
@@ -105,10 +107,13 @@ def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int 
         if n_batches == 0:
             raise RuntimeError("fit: the training loader is empty")
         for bi, batch in enumerate(train_loader):
+            window_end = (bi + 1) % acc == 0 or bi + 1 == n_batches   # windows restart every epoch; the last one may be short
             loss = step.training_step(batch)
+            if reducer is not None:
+                reducer.armed = window_end              # DDP's no_sync(): only the last micro-batch of a window reduces
             (loss / acc).backward()                     # Lightning divides the loss by accumulate_grad_batches
             last = float(loss.detach())
-            if (bi + 1) % acc == 0 or bi + 1 == n_batches:   # accumulation windows restart every epoch; the last one may be short
+            if window_end:
                 optimizer_step()
                 if gstep >= max_steps:
                     break
@@ -124,6 +129,8 @@ def fit(step, train_loader, config: dict, val_loader=None, log=print, rank: int 
                 if rank == 0:
                     log(f"epoch {epoch}: val/loss {tot / n:.5f}")
         epoch += 1
+    if reducer is not None:
+        reducer.remove()
     return {"steps": gstep, "last_loss": last, "val": val_hist, "epochs": epoch}
 
 
