@@ -13,10 +13,15 @@ tokens are denoised per step. Weights are random-init at the true 5B shapes, inp
 
 Printed JSON (rank 0): value = device-resident throughput (CUDA events); e2e = the same metric through the
 host-facing pipeline call with pinned host buffers (H2D of latents + prompt embeddings and D2H of the new
-latents inside the timed region); roofline = the attention kernel's FLOP/s against the measured cuBLAS
-bf16 peak; cpu_baseline = the CPU oracle on a bounded sample (one transformer block), extrapolated.
---impl reference times that CPU restatement of the reference's diffusers path on the host cores (diffusers
-itself is not installable offline).
+latents inside the timed region); roofline = the attention call's FLOP/s against the measured cuBLAS
+bf16 peak; cpu_baseline = the CPU oracle on a bounded sample (one transformer block), extrapolated;
+gpu_eager_baseline = the same step through plain torch (cuBLAS + SDPA) on the same GPU.
+Secondary legs (bench_legs.py): at N = 1 the scorer kernels (MVCS = BASELINE.json's second headline metric, reprojection,
+DPO loss), each with its own roofline object and a cpu_baseline that runs the reference's own file from oracle/_ref
+(kind "reference"); at N >= 2 the multi-GPU splits of north_star under "multi_gpu": CFG-pair shard (CogVideoX and
+Wan2.2), the prompt-sharded clip with VAE decode and frame gather, and the DPO step under DDP.
+--impl reference times the CPU restatement of the reference's diffusers path on the host cores (diffusers
+itself is not installable offline) and the reference's own scorer files.
 """
 from __future__ import annotations
 
@@ -125,14 +130,23 @@ def run_reference(args, rank):
         v, sec_block, desc = cpu_block_sample(threads)
         vals.append(v)
     value = sum(vals) / len(vals)
+    try:
+        import bench_legs
+        scorer = bench_legs.cpu_scorer_baselines()
+    except Exception as ex:      # noqa: BLE001
+        scorer = {"error": f"{type(ex).__name__}: {ex}"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * S_VIDEO / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "layers": 42, "tokens_per_step_per_gpu": S_VIDEO, "sequence": S_TEXT + S_VIDEO,
                        "note": "CPU arm: oracle/dit_torch.py restatement of the reference's diffusers path on the host cores "
                                "(diffusers/peft are not installable offline, DESIGN.md); each step = a bounded sample, see cpu_baseline.sample"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
+                             "sample_fraction_of_a_step": 1.0 / 84.0},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            # the scorer half of the path CAN run the reference's own files on this box (oracle/_ref, byte-compiled from
+            # /root/reference): MVCS (BASELINE.json's second metric), project_points, DPOLoss
+            "secondary": scorer,
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0}
     print(json.dumps(line), flush=True)
 
@@ -141,8 +155,8 @@ def run_reference(args, rank):
 def run_ours(args, rank, world, local):
     import torch
     import torch.distributed as dist
+    import bench_legs
     from videogpa_b200 import _lib, dense
-    from videogpa_b200.metrics import mvcs_batch
     from videogpa_b200.pipeline import CogVideoXDenoisePipeline
     from videogpa_b200.schedulers import CogVideoXDDIMScheduler
     from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
@@ -249,6 +263,13 @@ def run_ours(args, rank, world, local):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    # ---- the multi-GPU splits north_star names (every rank takes part; rank 0 reports)
+    multi = None
+    if world >= 2 and world % 2 == 0 and not args.no_multi_gpu_legs:
+        try:
+            multi = bench_legs.multi_gpu_legs(args, rank, world, dev, model, pipe, ms_max / args.steps)
+        except Exception as ex:         # noqa: BLE001
+            multi = {"error": f"{type(ex).__name__}: {ex}"}
     if rank != 0:
         return
     tokens = world * S_VIDEO * args.steps
@@ -270,42 +291,31 @@ def run_ours(args, rank, world, local):
         "ln_modulate_kernel": {"launches": len(ln_events), "share_of_step": ln_ms / ms_max if ms_max > 0 else None,
                                "achieved_gbs": ln_bytes / (ln_ms / 1000.0) / 1e9 if ln_ms > 0 else None, "peak_gbs": peak_hbm},
     }
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "attention_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    traffic = bench_legs.measured_traffic("attn_fwd_d64_bounded_kernel")
 
-    # ---- secondary metric of BASELINE.json: MVCS scores/s at the DA3 production size, batched
-    mvcs = None
-    try:
-        if world > 1:
-            raise RuntimeError("reported at N = 1 only")
-        N, T, H, W = 128, 10, 504, 504
-        gd = torch.Generator(device=dev).manual_seed(0)
-        depth = 2.0 + 0.5 * torch.rand(N, T, H, W, generator=gd, device=dev)
-        K = torch.tensor([[0.8 * W, 0, W / 2], [0, 0.8 * W, H / 2], [0, 0, 1]], device=dev).expand(N, T, 3, 3).contiguous()
-        E = torch.zeros(N, T, 3, 4, device=dev)
-        import math
-        for i in range(T):
-            a = math.radians(0.5 * i)
-            E[:, i] = torch.tensor([[math.cos(a), 0, math.sin(a), 0.02 * i], [0, 1, 0, 0], [-math.sin(a), 0, math.cos(a), 0]], device=dev)
-        for _ in range(3):
-            mvcs_batch(depth, K, E)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(5):
-            sc = mvcs_batch(depth, K, E)
-        a1.record(); torch.cuda.synchronize()
-        mms = a0.elapsed_time(a1) / 5
-        mvcs = {"metric": "MVCS scores/sec", "value": N / (mms / 1000.0), "unit": "scores/s", "clips_per_launch": N,
-                "workload": "10 frames 504x504 (DA3 production size), synthetic depth/pose", "ms_per_launch": mms,
-                "hbm_gbs_algorithmic": N * (T - 1) * H * W * 8 / (mms / 1000.0) / 1e9, "hbm_peak_gbs": peak_hbm,
-                "score0": float(sc[0].item())}
-        del depth
-    except Exception as ex:     # the secondary metric never hides the primary line
-        mvcs = {"error": str(ex)}
+    # ---- the scorer kernels: MVCS (BASELINE.json's second headline metric), reprojection, DPO loss, each with its own roofline and
+    #      a CPU baseline that runs the reference's own file (oracle/_ref) on this box's host cores
+    scorer_cpu, scorer = None, None
+    if world == 1:
+        if not args.no_cpu_baseline:
+            try:
+                scorer_cpu = bench_legs.cpu_scorer_baselines()
+            except Exception as ex:     # noqa: BLE001
+                scorer_cpu = {"error": f"{type(ex).__name__}: {ex}"}
+        try:
+            scorer = bench_legs.gpu_scorer_legs(dev, peak_hbm, scorer_cpu)
+        except Exception as ex:         # the secondary metric never hides the primary line
+            scorer = {"mvcs": {"error": f"{type(ex).__name__}: {ex}"}}
+    mvcs = (scorer or {}).get("mvcs") if world == 1 else {"error": "reported at N = 1 only"}
+
+    # ---- the same step through plain torch on the same GPU (cuBLAS + SDPA + eager elementwise kernels)
+    eager = None
+    if world == 1 and not args.no_gpu_eager:
+        try:
+            eager = bench_legs.gpu_eager_baseline(dev)
+            eager["speedup_of_this_repo"] = value / eager["value"]
+        except Exception as ex:         # noqa: BLE001
+            eager = {"error": f"{type(ex).__name__}: {ex}"}
 
     # ---- VAE decode of the finished clip (part of the same path; reported separately)
     vae = None
@@ -447,12 +457,15 @@ def run_ours(args, rank, world, local):
                    "parallelism": f"dp{world} (prompt shard, no data-path collective)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps},
         "gpu_launches": args.steps * (model.kernel_launches(2) + 1),
-        "roofline": {"kernel": "attn_fwd_d64_kernel", "bound": "tensor", "achieved": attn_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "roofline": {"kernel": "attn_fwd_d64_bounded_kernel", "bound": "tensor", "achieved": attn_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": attn_tf / peak_tf, "traffic": traffic, "peak_source": peak_src + " bf16_tflops_sustained",
                      "flops_per_launch": attn_flops, "avg_launch_ms": attn_avg_ms, "launches_timed": len(attn_ms),
-                     "share_of_step": (sum(attn_ms) / ms_max) if ms_max > 0 else None},
+                     "share_of_step": (sum(attn_ms) / ms_max) if ms_max > 0 else None,
+                     "note": "time = the whole vgpa_attention_bf16 call inside the timed steps: |q|,|k| bound pre-pass + bounded-softmax kernel "
+                             "+ the (empty) exact-kernel launch; traffic = ncu dram bytes of the main kernel, null if the capture is from another source version"},
         "step_tflops": step_flops * args.steps / (ms_max / 1000.0) / 1e12, "kernel_families": families,
-        "cpu_baseline": cpu, "clocks": clocks, "finite": finite, "secondary": mvcs, "vae_decode": vae, "encoders": enc_leg, "wan_step": wan, "dpo_train_step": train,
+        "cpu_baseline": cpu, "gpu_eager_baseline": eager, "clocks": clocks, "finite": finite, "secondary": mvcs,
+        "scorer_kernels": {k: v for k, v in (scorer or {}).items() if k != "mvcs"} or None, "multi_gpu": multi, "vae_decode": vae, "encoders": enc_leg, "wan_step": wan, "dpo_train_step": train,
     }
     print(json.dumps(line), flush=True)
 
@@ -465,6 +478,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=0, help="debug: run fewer transformer blocks (the number is printed in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager GPU baseline of the step (N = 1)")
+    ap.add_argument("--no-multi-gpu-legs", action="store_true", help="N >= 2: skip the CFG-pair / clip / DDP legs")
+    ap.add_argument("--e2e-steps", type=int, default=50, help="N >= 2: denoise steps of the prompt-sharded clip leg")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

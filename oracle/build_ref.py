@@ -3,7 +3,7 @@
     python -m oracle.build_ref          # in the build container, where /root/reference is mounted
 
 The reference is Python, so "compiling its own few source files" is `py_compile`: the files below are byte-compiled
-straight from /root/reference into oracle/_ref/*.pyc. No reference SOURCE enters the repository: oracle/_ref/ is
+straight from /root/reference into oracle/_ref/*.refbc. No reference SOURCE enters the repository: oracle/_ref/ is
 git-ignored (built artefact, like our own .so files) but not gpurun-ignored, so the bytecode travels to the GPU box and
 `bench.py` can time the reference's own implementation on that box's host cores (`cpu_baseline.kind = "reference"`,
 `--impl reference`), which /root/reference itself cannot do because it does not exist there. Only bench.py's CPU legs and
@@ -40,7 +40,7 @@ def build(verbose: bool = False) -> bool:
     manifest = {"python": sys.version.split()[0], "files": {}}
     for name, rel in FILES.items():
         src = REF / rel
-        dst = OUT / f"{name}.pyc"
+        dst = OUT / f"{name}.refbc"
         py_compile.compile(str(src), cfile=str(dst), dfile=f"<reference>/{rel}", doraise=True)
         manifest["files"][name] = rel
         if verbose:

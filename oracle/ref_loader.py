@@ -45,10 +45,10 @@ def load():
                 pkg = types.ModuleType("metrics")
                 pkg.__path__ = []
                 sys.modules["metrics"] = pkg
-            _load_pyc("metrics.base", REF_DIR / "metrics_base.pyc")
-            mvcs = _load_pyc("metrics.mvcs", REF_DIR / "metrics_mvcs.pyc")
-            proj = _load_pyc("_ref_projection_utils", REF_DIR / "utils_projection_utils.pyc")
-            loss = _load_pyc("_ref_train_loss", REF_DIR / "train_loss.pyc")
+            _load_pyc("metrics.base", REF_DIR / "metrics_base.refbc")
+            mvcs = _load_pyc("metrics.mvcs", REF_DIR / "metrics_mvcs.refbc")
+            proj = _load_pyc("_ref_projection_utils", REF_DIR / "utils_projection_utils.refbc")
+            loss = _load_pyc("_ref_train_loss", REF_DIR / "train_loss.refbc")
             ns = types.SimpleNamespace(MVCSMetric=mvcs.MVCSMetric, project_points=proj.project_points,
                                        batch_reproject=getattr(proj, "batch_reproject", None), DPOLoss=loss.DPOLoss,
                                        create_loss_strategy=loss.create_loss_strategy)
