@@ -263,15 +263,55 @@ def run_ours(args, rank, world, local):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max = float(times[0]), float(times[1])
-    # ---- the multi-GPU splits north_star names (every rank takes part; rank 0 reports)
+    # ---- the multi-GPU splits north_star names (every rank takes part; rank 0 reports). The legs run collectives, so a rank
+    #      that fails alone (e.g. out of memory) would leave its peers waiting: a watchdog on every rank bounds the legs, and on
+    #      expiry rank 0 prints the primary line (already measured) with the legs finished so far and every rank exits.
     multi = None
     if world >= 2 and world % 2 == 0 and not args.no_multi_gpu_legs:
+        multi = {}
+        done = threading.Event()
+
+        def watchdog():
+            if done.wait(args.multi_gpu_timeout):
+                return
+            if rank == 0:
+                m = dict(multi)
+                m["error"] = f"multi-GPU legs did not finish within {args.multi_gpu_timeout:.0f} s; the legs listed here had completed"
+                try:
+                    emit(m, on_timeout=True)
+                finally:
+                    os._exit(0)
+            time.sleep(5.0)
+            os._exit(0)
+
+        wd = threading.Thread(target=watchdog, daemon=True)
+    else:
+        wd = None
+
+    def emit(multi, on_timeout=False):
+        _emit_line(args, world, ms_max, e2e_ms_max, cfg, model, attn_ms, lin_events, ln_events, lat, finite, h2d, d2h, clocks, dev, multi,
+                   on_timeout)
+
+    if wd is not None:
+        wd.start()
         try:
-            multi = bench_legs.multi_gpu_legs(args, rank, world, dev, model, pipe, ms_max / args.steps)
+            bench_legs.multi_gpu_legs(args, rank, world, dev, model, pipe, ms_max / args.steps, out=multi)
         except Exception as ex:         # noqa: BLE001
-            multi = {"error": f"{type(ex).__name__}: {ex}"}
+            multi["error"] = f"{type(ex).__name__}: {ex}"
+        done.set()
     if rank != 0:
         return
+    emit(multi)
+
+
+def _emit_line(args, world, ms_max, e2e_ms_max, cfg, model, attn_ms, lin_events, ln_events, lat, finite, h2d, d2h, clocks, dev, multi,
+               on_timeout=False):
+    """Rank 0: the secondary N = 1 legs and the JSON line."""
+    import torch
+    import bench_legs
+    guidance = 6.0
+    if on_timeout:                      # the device may be wedged in a collective: no further CUDA work
+        lin_events, ln_events = [], []
     tokens = world * S_VIDEO * args.steps
     value = tokens / (ms_max / 1000.0)
     e2e_value = tokens / (e2e_ms_max / 1000.0)
@@ -481,6 +521,7 @@ def main():
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager GPU baseline of the step (N = 1)")
     ap.add_argument("--no-multi-gpu-legs", action="store_true", help="N >= 2: skip the CFG-pair / clip / DDP legs")
     ap.add_argument("--e2e-steps", type=int, default=50, help="N >= 2: denoise steps of the prompt-sharded clip leg")
+    ap.add_argument("--multi-gpu-timeout", type=float, default=420.0, help="N >= 2: bound (s) on the multi-GPU legs before the line is printed without them")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -222,14 +222,14 @@ def _max_over_ranks(vals, dev):
     return [float(v) for v in t]
 
 
-def multi_gpu_legs(args, rank: int, world: int, dev, model, pipe, single_gpu_step_ms: float) -> dict:
+def multi_gpu_legs(args, rank: int, world: int, dev, model, pipe, single_gpu_step_ms: float, out: dict | None = None) -> dict:
     """world >= 2 (even): (i) CFG-pair shard of the CogVideoX step and of the Wan2.2 step, (ii) BASELINE.json configs[2]
     end to end (50 steps + VAE decode + frame gather), (iii) the DPO step under DDP. All times are CUDA events, max over ranks."""
     import torch
     import torch.distributed as dist
     from videogpa_b200.parallel import (BucketedGradReducer, CfgPairGroup, CfgPairPeerGroup, gather_frames)
     BF = torch.bfloat16
-    out = {}
+    out = {} if out is None else out                     # filled leg by leg, so a watchdog can report the legs that finished
 
     def barrier():
         dist.barrier()

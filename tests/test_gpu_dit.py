@@ -177,6 +177,26 @@ def test_lora_merge_vs_oracle(lib, tmp_path):
         assert (got != ref).float().mean() < 0.01 and diff.max() <= 2.0 ** -7 * ref.float().abs().max()   # <= 1 bf16 ulp
     with pytest.raises(RuntimeError):
         merge_lora(model, str(tmp_path / "missing"))
+    # re-scalable attachment (replicate.py:208-213: module.scaling = w * alpha / r per work item, adapter never merged)
+    from videogpa_b200.lora import attach_lora
+    merged = {k: model.attention_weight(*k).clone() for k in expect}
+    fresh = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
+    base = {k: fresh.attention_weight(*k).clone() for k in expect}
+    h = attach_lora(fresh, str(tmp_path))                            # weight 1.0 = alpha / r: the bits of merge_lora
+    assert len(h) == 8 and h.scaling == 2.0
+    assert all(torch.equal(fresh.attention_weight(*k), merged[k]) for k in expect)
+    for w in (0.2, 0.5, 0.2):                                        # any order of strengths: always one rounding from the base
+        h.set_weight(w)
+        for (layer, mod) in expect:
+            A, Bm = pairs[(layer, mod)]
+            ref = O.lora_merge(sd[f"transformer_blocks.{layer}.attn1.{mod}.weight"], A, Bm, w * 2.0)
+            got = fresh.attention_weight(layer, mod).cpu()
+            assert (got != ref).float().mean() < 0.01 and (got.float() - ref.float()).abs().max() <= 2.0 ** -7 * ref.float().abs().max()
+    first = {k: fresh.attention_weight(*k).clone() for k in expect}
+    h.set_weight(0.2)
+    assert all(torch.equal(fresh.attention_weight(*k), first[k]) for k in expect)          # no drift
+    h.unmerge()
+    assert all(torch.equal(fresh.attention_weight(*k), base[k]) for k in expect)           # base weights restored exactly
 
 
 def test_scheduler_step_vs_oracle(lib):

@@ -152,6 +152,14 @@ def test_motion_mse_unproject(lib, golden):
     assert isinstance(val, float) and abs(motion - float(g["motion_kat"])) < 1e-6 and val > float(g["mse_kat"])
     with pytest.raises(RuntimeError):
         Consistency_Score(device="cuda").compute(gt=cuda(g["mse_gt"]), rep=cuda(g["mse_rep"]), extrinsics=cuda(g["motion_E"]))
+    # metrics/lpips.py:56-62: numpy frames are always divided by 255 (a dark uint8 clip with max <= 1 too), and
+    # consistency_score.py:68-71 evaluates LPIPS whatever the ratio
+    seen = []
+    cs2 = Consistency_Score(lpips_net=lambda a, b: (seen.append((a, b)), (a - b).abs().mean(dim=(1, 2, 3)))[1], device="cuda")
+    dark = np.zeros((2, 8, 8, 3), dtype=np.uint8); dark[0, 0, 0, 0] = 1
+    rep_small = cuda(g["mse_rep"])[:2, :, :8, :8].contiguous()
+    cs2.compute(gt=dark, rep=rep_small, extrinsics=cuda(g["motion_E"]), ratio=0)
+    assert len(seen) == 1 and abs(float(seen[0][0].max()) - (2.0 / 255.0 - 1.0)) < 1e-7 and float(seen[0][0].min()) == -1.0
     gg = golden("geometry")
     wp = unproject_depth(cuda(gg["depth"]), cuda(gg["K"]), cuda(gg["E4"])).cpu().numpy()
     assert np.abs(wp - gg["world_points"]).max() < 2e-6               # vs DA3 geometry.py

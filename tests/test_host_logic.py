@@ -49,6 +49,30 @@ def test_scheduler_tables_match_oracle():
     assert torch.allclose(s.get_velocity(x, n, t), O.get_velocity(ac, x, n, t.numpy()))
 
 
+def test_scheduler_from_checkpoint_config(tmp_path):
+    """generate/CogVideoX-5B.py:18 (`from_config(pipe.scheduler.config, timestep_spacing="trailing")`) and
+    train/CogVideoX-5B/03_train.py:113 (`from_pretrained(model_path, subfolder="scheduler")`): the checkpoint's own betas and
+    snr_shift_scale decide the noise levels (CogVideoX-2B ships snr_shift_scale 3.0)."""
+    from videogpa_b200.schedulers import CogVideoXDDIMScheduler, CogVideoXDPMScheduler
+    cfg = {"_class_name": "CogVideoXDDIMScheduler", "_diffusers_version": "0.30.0", "beta_start": 0.00085, "beta_end": 0.012,
+           "beta_schedule": "scaled_linear", "clip_sample": False, "num_train_timesteps": 1000, "prediction_type": "v_prediction",
+           "rescale_betas_zero_snr": True, "set_alpha_to_one": True, "snr_shift_scale": 3.0, "steps_offset": 0,
+           "timestep_spacing": "linspace", "trained_betas": None}
+    (tmp_path / "scheduler").mkdir()
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(cfg))
+    d = CogVideoXDPMScheduler.from_pretrained(str(tmp_path), timestep_spacing="trailing")
+    assert np.array_equal(d.alphas_cumprod, O.cogvideox_alphas_cumprod(snr_shift_scale=3.0))
+    assert not np.array_equal(d.alphas_cumprod, CogVideoXDPMScheduler().alphas_cumprod)
+    s = CogVideoXDDIMScheduler.from_config(dict(cfg, snr_shift_scale=1.0, timestep_spacing="trailing"))
+    assert np.array_equal(s.alphas_cumprod, CogVideoXDDIMScheduler().alphas_cumprod)
+    with pytest.raises(RuntimeError):
+        CogVideoXDDIMScheduler.from_config(cfg)                                  # linspace spacing is not implemented: loud, not silent
+    with pytest.raises(RuntimeError):
+        CogVideoXDDIMScheduler.from_config(dict(cfg, timestep_spacing="trailing", prediction_type="epsilon"))
+    with pytest.raises(RuntimeError):
+        CogVideoXDPMScheduler.from_pretrained(str(tmp_path / "missing"))
+
+
 def test_rope_table_matches_oracle():
     from videogpa_b200.rope import get_3d_rotary_pos_embed
     cfg = O.DiTConfig()

@@ -134,7 +134,9 @@ def build_pipeline(args, device, with_encoder: bool = False):
         prompts = _T5Prompts(base, device)
     vae.enable_tiling()
     vae.enable_slicing()
-    pipe = CogVideoXDenoisePipeline(transformer, CogVideoXDPMScheduler(), vae=vae, vae_scaling_factor=vae.config.scaling_factor)
+    # :18 `CogVideoXDPMScheduler.from_config(pipe.scheduler.config, timestep_spacing="trailing")`: betas / snr_shift_scale of the checkpoint
+    scheduler = CogVideoXDPMScheduler() if args.synthetic else CogVideoXDPMScheduler.from_pretrained(args.base_model, timestep_spacing="trailing")
+    pipe = CogVideoXDenoisePipeline(transformer, scheduler, vae=vae, vae_scaling_factor=vae.config.scaling_factor)
     pipe.vae_encoder = None
     if with_encoder:
         from ..vae import AutoencoderKLCogVideoXEncoder

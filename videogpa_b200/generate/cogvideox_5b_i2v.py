@@ -94,7 +94,17 @@ def generate(args):
         prompts = base._SyntheticPrompts(cfg.text_embed_dim, device)
     else:
         pipe, prompts = base.build_pipeline(args, device, with_encoder=True)
-        pipe.scheduler = CogVideoXDDIMScheduler()                   # the I2V script keeps the checkpoint default (:18-19)
+        # the I2V script keeps the checkpoint's own scheduler (:16-19, no swap): class and settings from scheduler_config.json
+        import json
+        from ..schedulers import CogVideoXDPMScheduler
+        sc_file = Path(args.base_model) / "scheduler" / "scheduler_config.json"
+        if not sc_file.is_file():
+            raise RuntimeError(f"{sc_file} not found")
+        sc = json.loads(sc_file.read_text())
+        known = {"CogVideoXDDIMScheduler": CogVideoXDDIMScheduler, "CogVideoXDPMScheduler": CogVideoXDPMScheduler}
+        if sc.get("_class_name", "CogVideoXDDIMScheduler") not in known:
+            raise RuntimeError(f"scheduler class {sc.get('_class_name')!r} is not implemented")
+        pipe.scheduler = known[sc.get("_class_name", "CogVideoXDDIMScheduler")].from_config(sc)
     if args.lora_path:
         if not os.path.exists(args.lora_path):
             print(f"LoRA path not found: {args.lora_path}, using base model")

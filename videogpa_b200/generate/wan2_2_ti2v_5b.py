@@ -13,7 +13,8 @@ shifted flow-matching schedule (`--shift`) and the UniPC multistep sampler that 
 repository's umT5 text encoder and Wan-VAE are outside this build, so the result of a prompt is the final latent
 `seed_<seed>.latents.pt` ([48, F, h, w], bf16) instead of an mp4, and inputs are either synthetic (`--synthetic N`: N-block
 random DiT, context / first-frame latent seeded from the prompt and image bytes) or precomputed next to the image:
-`<image>.context.pt` ([L <= 512, 4096]) and `<image>.latent.pt` ([48, 1, h, w]).
+`<image>.context.pt` ([L <= 512, 4096]), `<image>.latent.pt` ([48, 1, h, w]) and the encoded negative prompt
+`<image>.null_context.pt` (or one shared `<model_path>/null_context.pt`) for the unconditional branch.
 """
 from __future__ import annotations
 
@@ -59,7 +60,9 @@ class WanTI2VEngine:
 
     @torch.no_grad()
     def generate(self, context, first_latent, frame_num=81, shift=5.0, sampling_steps=50, guide_scale=5.0, seed=42, size=(704, 1280),
-                 sample_solver="unipc"):
+                 sample_solver="unipc", null_context=None):
+        """null_context: the umT5 encoding of the configured negative prompt (`sample_neg_prompt`), which `WanTI2V.generate`
+        feeds to the unconditional branch; None = a single all-zero token (only meaningful for synthetic runs)."""
         from ..wan import flow_sigmas
         F_, h, w, S = latent_grid(frame_num, size[0], size[1])
         if tuple(first_latent.shape) != (self.model.config.in_dim, 1, h, w):
@@ -70,7 +73,10 @@ class WanTI2VEngine:
         lat[:, :1] = first
         hw = (h // 2) * (w // 2)
         step = self._step(self.model, guide_scale=guide_scale)
-        null = torch.zeros(1, context.shape[-1], device=self.device, dtype=BF16)
+        if null_context is None:
+            null = torch.zeros(1, context.shape[-1], device=self.device, dtype=BF16)
+        else:
+            null = null_context.to(device=self.device, dtype=BF16)
         ctx = context.to(device=self.device, dtype=BF16)
         if sample_solver == "unipc":                                   # WanTI2V.generate's default sampler
             from ..schedulers import FlowUniPCMultistepScheduler
@@ -78,7 +84,7 @@ class WanTI2VEngine:
             sch.set_timesteps(sampling_steps, shift=shift)
             x = lat.float()
             for i in range(sampling_steps):
-                t = torch.full((1, S), float(sch.timesteps[i]))
+                t = torch.full((1, S), float(int(sch.timesteps[i])))    # Wan's FlowUniPC scheduler hands the model int64 timesteps
                 t[:, :hw] = 0                                          # the image frame is clean: t = 0 for its tokens
                 v = step.guided_velocity(x, t, ctx, null)
                 x = sch.step(v, x)
@@ -182,8 +188,18 @@ def generate(args):
                 if not cpath.exists() or not lpath.exists():
                     raise RuntimeError(f"{cpath.name} / {lpath.name} not found: umT5 and the Wan-VAE are outside this build")
                 context, first = torch.load(str(cpath), map_location="cpu"), torch.load(str(lpath), map_location="cpu")
+                # the unconditional branch sees the encoded negative prompt: per image, else one shared file in the model directory
+                npath = Path(str(image_path) + ".null_context.pt")
+                if not npath.exists():
+                    npath = Path(args.model_path) / "null_context.pt"
+                if not npath.exists():
+                    raise RuntimeError(f"{Path(str(image_path)).name}.null_context.pt / {npath} not found: the umT5 encoding of the "
+                                       "negative prompt is needed for the unconditional branch")
+                null_context = torch.load(str(npath), map_location="cpu")
+            if args.synthetic:
+                null_context = _seeded("negative prompt", (32, cfg.text_dim), "txt")
             lat = engine.generate(context, first, frame_num=args.frame_num, shift=args.shift, sampling_steps=args.sampling_steps,
-                                  guide_scale=args.guide_scale, seed=args.seed, size=(args.height, args.width))
+                                  guide_scale=args.guide_scale, seed=args.seed, size=(args.height, args.width), null_context=null_context)
             torch.save(lat.cpu(), str(out_path))
         except Exception as e:                      # noqa: BLE001
             print(f"  Failed: {e}")

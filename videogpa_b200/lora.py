@@ -65,6 +65,20 @@ def _split_bf16(t: torch.Tensor):
     return hi, lo
 
 
+def _check_shapes(layer, module, A, B, W):
+    if B.shape[0] != W.shape[0] or A.shape[1] != W.shape[1] or A.shape[0] != B.shape[1]:
+        raise RuntimeError(f"LoRA shape mismatch at layer {layer} {module}: A {tuple(A.shape)} B {tuple(B.shape)} W {tuple(W.shape)}")
+
+
+def _delta_operands(A: torch.Tensor, B: torch.Tensor):
+    """fp32 A [r, in], B [out, r] -> bf16 GEMM operands ([out, 3r], [in, 3r]) whose product is B @ A to ~2^-16."""
+    Bh, Bl = _split_bf16(B)
+    Ah, Al = _split_bf16(A.t().contiguous())                                 # [in, r]
+    a_op = torch.cat([Bh, Bh, Bl], dim=1).contiguous()                       # [out, 3r]
+    w_op = torch.cat([Ah, Al, Ah], dim=1).contiguous()                       # [in, 3r]  (N = in features)
+    return a_op, w_op
+
+
 def merge_lora(transformer, lora_path: str, scaling: float | None = None, weight: float | None = None) -> int:
     """Merge the adapter into `transformer` in place. scaling = absolute override; weight multiplies alpha/r.
 
@@ -83,12 +97,68 @@ def merge_lora(transformer, lora_path: str, scaling: float | None = None, weight
         W = transformer.attention_weight(layer, module)                      # [out, in] bf16 view, updated in place
         A = A.to(device=dev, dtype=torch.float32)                            # [r, in]
         B = B.to(device=dev, dtype=torch.float32)                            # [out, r]
-        if B.shape[0] != W.shape[0] or A.shape[1] != W.shape[1] or A.shape[0] != B.shape[1]:
-            raise RuntimeError(f"LoRA shape mismatch at layer {layer} {module}: A {tuple(A.shape)} B {tuple(B.shape)} W {tuple(W.shape)}")
-        Bh, Bl = _split_bf16(B)
-        Ah, Al = _split_bf16(A.t().contiguous())                             # [in, r]
-        a_op = torch.cat([Bh, Bh, Bl], dim=1).contiguous()                   # [out, 3r]
-        w_op = torch.cat([Ah, Al, Ah], dim=1).contiguous()                   # [in, 3r]  (N = in features)
+        _check_shapes(layer, module, A, B, W)
+        a_op, w_op = _delta_operands(A, B)
         dense.linear(a_op, w_op, None, out=W, epilogue=dense.EPI_ACCUM, alpha=s)
         n += 1
     return n
+
+
+class AttachedLoRA:
+    """An adapter whose strength can be changed or removed after loading.
+
+    Reference: replicate.py:208-213 keeps the PEFT adapter unmerged and, per work item, sets
+    `module.scaling[name] = lora_weight * lora_alpha / r` on every LoRA layer before generating. Here the targeted base
+    weights (3.2 GB bf16 for CogVideoX-5B: a rounding error of the 180 GB) are kept pristine on the device next to the split
+    adapter operands, and every change of strength rebuilds W = round_bf16(W_base + s * B @ A) from the pristine copy with
+    the same accumulate-epilogue GEMM as `merge_lora`: one rounding, no drift however often the strength changes, and the
+    denoise step keeps running on plain fused weights. `set_scaling(s)` with s equal to merge_lora's gives the same bits as
+    `merge_lora`; `unmerge()` restores the base weights exactly.
+    """
+
+    def __init__(self, transformer, lora_path: str):
+        self.transformer = transformer
+        self.config, pairs = read_adapter(lora_path)
+        self.r = int(self.config["r"])
+        self.lora_alpha = float(self.config["lora_alpha"])
+        self.scaling = 0.0                                                   # what is currently folded into the weights
+        dev = transformer.device
+        self._items = []
+        for (layer, module), (A, B) in sorted(pairs.items()):
+            if layer >= len(transformer.blocks):
+                raise RuntimeError(f"adapter targets layer {layer}, the model has {len(transformer.blocks)}")
+            W = transformer.attention_weight(layer, module)
+            A = A.to(device=dev, dtype=torch.float32)
+            B = B.to(device=dev, dtype=torch.float32)
+            _check_shapes(layer, module, A, B, W)
+            a_op, w_op = _delta_operands(A, B)
+            self._items.append((W, W.clone(), a_op, w_op))
+
+    def __len__(self) -> int:
+        return len(self._items)
+
+    def set_scaling(self, scaling: float) -> None:
+        """Absolute strength s (PEFT's `module.scaling`): W <- W_base + s * B @ A."""
+        s = float(scaling)
+        for W, base, a_op, w_op in self._items:
+            W.copy_(base)
+            if s != 0.0:
+                dense.linear(a_op, w_op, None, out=W, epilogue=dense.EPI_ACCUM, alpha=s)
+        self.scaling = s
+
+    def set_weight(self, lora_weight: float) -> None:
+        """replicate.py:208-213: scaling = lora_weight * lora_alpha / r."""
+        self.set_scaling(float(lora_weight) * self.lora_alpha / self.r)
+
+    def unmerge(self) -> None:
+        """Back to the base weights (bit-exact)."""
+        self.set_scaling(0.0)
+
+
+def attach_lora(transformer, lora_path: str, weight: float | None = 1.0) -> AttachedLoRA:
+    """Load an adapter re-scalably; `weight` (default 1.0 = alpha / r, what PEFT loads with) is applied at once, None leaves
+    the base weights untouched until set_scaling / set_weight is called."""
+    h = AttachedLoRA(transformer, lora_path)
+    if weight is not None:
+        h.set_weight(weight)
+    return h

@@ -159,20 +159,25 @@ class Consistency_Score(Metric):
             if t.shape[-1] == 3:
                 t = t.permute(0, 3, 1, 2)
             t = t.to(self.device)
-            if isinstance(x, np.ndarray):
-                return (t / 255.0 if t.max() > 1.0 else t) * 2.0 - 1.0
+            if isinstance(x, np.ndarray):                  # :56-62: numpy frames are always taken as 0-255
+                return (t / 255.0) * 2.0 - 1.0
             if t.min() >= 0:
                 if t.max() > 1.0:
                     t = t / 255.0
                 t = t * 2.0 - 1.0
             return t
 
+        gt_t, rep_t = to_pm1(gt), to_pm1(rep)
+        if gt_t.shape[-2:] != rep_t.shape[-2:]:            # :30-31 (torch's own resampling, as in the reference; LPIPS is third-party here)
+            rep_t = torch.nn.functional.interpolate(rep_t, size=gt_t.shape[-2:], mode="bilinear", align_corners=False)
         with torch.no_grad():
-            return float(self.lpips_net(to_pm1(gt), to_pm1(rep)).mean().item())
+            return float(self.lpips_net(gt_t, rep_t).mean().item())
 
     def compute(self, *, gt, rep, extrinsics, ratio=1, **kwargs):
         val_mse = self.mse_metric.compute(gt=gt, rep=rep)
-        val_lpips = self._lpips(gt, rep) if ratio != 0 else 0.0
+        # the reference always evaluates LPIPS (consistency_score.py:68-71), so a NaN there reaches the score even at ratio 0;
+        # only without an injected network (the VGG weights are not part of this package) is ratio = 0 a way to skip the term
+        val_lpips = 0.0 if (self.lpips_net is None and ratio == 0) else self._lpips(gt, rep)
         motion = compute_motion_score_vectorized(extrinsics, device=self.device)
         return float(val_mse + ratio * val_lpips), float(motion)
 

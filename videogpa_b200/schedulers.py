@@ -39,6 +39,35 @@ class _Base:
         self.timesteps = None
         self.num_inference_steps = None
 
+    _CONFIG_KEYS = ("num_train_timesteps", "beta_start", "beta_end", "snr_shift_scale", "timestep_spacing")
+
+    @classmethod
+    def from_config(cls, config: dict, **overrides):
+        """diffusers' `Scheduler.from_config(pipe.scheduler.config, timestep_spacing="trailing")` (generate/CogVideoX-5B.py:18):
+        the checkpoint's betas / snr_shift_scale decide alphas_cumprod (CogVideoX-2B ships snr_shift_scale 3.0, 5B 1.0).
+        Settings this implementation cannot honour raise instead of silently producing other noise levels."""
+        cfg = dict(config)
+        cfg.update(overrides)
+        if cfg.get("beta_schedule", "scaled_linear") != "scaled_linear":
+            raise RuntimeError(f"beta_schedule {cfg['beta_schedule']!r} is not implemented (CogVideoX uses scaled_linear)")
+        if cfg.get("prediction_type", "v_prediction") != "v_prediction":
+            raise RuntimeError(f"prediction_type {cfg['prediction_type']!r} is not implemented (CogVideoX uses v_prediction)")
+        if not cfg.get("rescale_betas_zero_snr", True):
+            raise RuntimeError("rescale_betas_zero_snr = false is not implemented (CogVideoX checkpoints set it)")
+        return cls(**{k: cfg[k] for k in cls._CONFIG_KEYS if k in cfg})
+
+    @classmethod
+    def from_pretrained(cls, model_dir, subfolder: str = "scheduler", **overrides):
+        """`from_pretrained(base, subfolder="scheduler")` (train/CogVideoX-5B/03_train.py:96-113): reads
+        <model_dir>/<subfolder>/scheduler_config.json."""
+        import json
+        import os
+        path = os.path.join(str(model_dir), subfolder, "scheduler_config.json")
+        if not os.path.isfile(path):
+            raise RuntimeError(f"{path} not found")
+        with open(path, "r", encoding="utf-8") as f:
+            return cls.from_config(json.load(f), **overrides)
+
     def set_timesteps(self, num_inference_steps: int, device=None):
         n = self.num_train_timesteps
         self.num_inference_steps = num_inference_steps

@@ -215,7 +215,12 @@ def main_train(config: dict, synthetic_layers: int = 0) -> dict:
             vae_encoder.enable_slicing()
         if config.get("enable_tiling"):
             vae_encoder.enable_tiling()
-    step = DPOSharedStep(transformer, None, beta=config["beta"], trainable=pol, vae_encoder=vae_encoder)
+    scheduler = None                                    # :113 CogVideoXDPMScheduler.from_pretrained(model_path, subfolder="scheduler")
+    if not synthetic_layers:
+        from ..schedulers import CogVideoXDPMScheduler
+        scheduler = CogVideoXDPMScheduler.from_pretrained(config["model_path"], subfolder="scheduler",
+                                                          timestep_spacing="trailing")     # add_noise / get_velocity only read alphas_cumprod
+    step = DPOSharedStep(transformer, None, beta=config["beta"], scheduler=scheduler, trainable=pol, vae_encoder=vae_encoder)
     ckpt = TopKCheckpoints(out_p / "checkpoints", pol.save_pretrained, top_k=int(config.get("save_top_k", 10))) if rank == 0 else None
     res = fit(step, train_loader, config, val_loader=val_loader, rank=rank, checkpoint_fn=ckpt)
     if rank == 0:
