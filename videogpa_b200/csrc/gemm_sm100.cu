@@ -19,7 +19,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
-constexpr int GROUP_M = 16;
+constexpr int GROUP_M_DEFAULT = 16;
 
 struct EpiParams {
   __nv_bfloat16* out;
@@ -41,6 +41,10 @@ struct EpiParams {
   const float* rope_sin;
   int model_dim;
   float alpha;
+  // rasterisation / L2 policy (host-chosen per launch)
+  int group_m;             // M tiles (tile pairs with a cluster) per raster group
+  int stream_out;          // 1: output stores carry the evict-first (streaming) hint
+  uint64_t hint_a, hint_w; // L2 eviction policy of the A / W operand loads
 };
 
 template <int BN>
@@ -195,7 +199,7 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
       o.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
       o.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]);
       o.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
-      op[i] = o;
+      if (ep.stream_out) __stcs(op + i, o); else op[i] = o;
     }
   }
 }
@@ -254,10 +258,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
-    const int per_group = GROUP_M * num_n;
+    const int per_group = ep.group_m * num_n;
     const int group = tile / per_group;
-    const int first_m = group * GROUP_M;
-    const int gsz = min(num_m - first_m, GROUP_M);
+    const int first_m = group * ep.group_m;
+    const int gsz = min(num_m - first_m, ep.group_m);
     const int in_group = tile - group * per_group;
     m_blk = (first_m + in_group % gsz) * CL + cta_rank;       // may be one past the last M tile: loads are zero-filled, stores masked
     n_blk = in_group / gsz;
@@ -274,12 +278,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nk; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-          ptx::tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          ptx::tma_load_2d_hint(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM, ep.hint_a);
           if (CL == 2) {
-            ptx::tma_load_2d_multicast(sB + stage * Cfg::B_BYTES + cta_rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * BK,
-                                       n_blk * BN + cta_rank * (BN / 2), 0x3);
+            ptx::tma_load_2d_multicast_hint(sB + stage * Cfg::B_BYTES + cta_rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], kb * BK,
+                                            n_blk * BN + cta_rank * (BN / 2), 0x3, ep.hint_w);
           } else {
-            ptx::tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            ptx::tma_load_2d_hint(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN, ep.hint_w);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -442,6 +446,19 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
   ep.rope_cos = a->rope_cos; ep.rope_sin = a->rope_sin;
   ep.model_dim = a->model_dim;
   ep.alpha = a->alpha;
+  // development knobs (read once): raster group height and L2 policies
+  static int k_group = -1, k_stream = -1, k_hints = -1;
+  if (k_group < 0) {
+    const char* e = getenv("VGPA_GEMM_GROUP_M");  k_group = e ? atoi(e) : GROUP_M_DEFAULT;
+    e = getenv("VGPA_GEMM_STREAM_OUT");           k_stream = e ? atoi(e) : 0;
+    e = getenv("VGPA_GEMM_HINTS");                k_hints = e ? atoi(e) : 0;
+    if (k_group < 1) k_group = GROUP_M_DEFAULT;
+  }
+  ep.group_m = k_group;
+  // in-place epilogues re-read what they store (residual / accumulate): never stream those
+  ep.stream_out = (k_stream && a->epilogue != VGPA_EPI_GATE_RES && a->epilogue != VGPA_EPI_ACCUM && a->epilogue != VGPA_EPI_GATE_RES_F32) ? 1 : 0;
+  ep.hint_a = (k_hints & 1) ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;     // the A group is what a raster group re-reads across N
+  ep.hint_w = (k_hints & 2) ? ptx::L2_EVICT_FIRST : ((k_hints & 4) ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL);
   if (a->epilogue == VGPA_EPI_QKV) {
     VGPA_CHECK(a->model_dim > 0 && a->model_dim % 64 == 0 && a->N == 3 * a->model_dim,
                "vgpa_linear_bf16: QKV epilogue needs N == 3*model_dim (N=%d model_dim=%d)", a->N, a->model_dim);

@@ -12,16 +12,20 @@
 //
 // Bit-exact mask counts at HBM speed. The in-image mask (mvcs.py:99) must match the reference / numpy oracle pixel for pixel,
 // which fixes the fp32 operation order of the whole projection chain (no FMA contraction: this file is compiled with
-// --fmad=false, IEEE division). Evaluated for every pixel that chain costs ~280 instructions and made the kernel
-// issue-bound at 0.15 of the HBM roofline. Only pixels whose projection lands within rounding distance of a mask boundary
-// can decide differently under another evaluation order, so every pixel first takes a FAST path: the three matrices are
-// merged per pair (M = K_j R K_i^-1 in fp64, rounded once), h = d (M [u,v,1]) + K_j t with explicit FMAs, one approximate
-// reciprocal. mvcs_prepare also derives a rigorous forward-error bound of BOTH evaluations against the real-valued result
-// (gamma_n sum |a_i b_i| with n = 32 >= the 12-op chain, at u <= W, v <= H): |dh_c| <= Bh_c d + Bt_c, which gives a per-pixel
-// margin on u_j, v_j, z_j. A pixel closer than the margin to u_j in {0, W}, v_j in {0, H}, z_j = 0 or the z clamp is
-// re-evaluated by `exact_pixel` (the reference's operation order); all other pixels provably take the same mask decision on
-// both paths. Sampled values differ by a few ulp between the paths (the tests allow 1e-5 on the per-pair MSE; the counts
-// stay exact). At 504 x 504 about 1 pixel in 10^4 takes the exact path.
+// --fmad=false, IEEE division). Evaluated for every pixel that chain costs ~280 instructions (0.15 of the HBM roofline).
+// Only pixels whose projection lands within rounding distance of a mask boundary can decide differently under another
+// evaluation order, so the work is tiered:
+//   tier 1 (mvcs_pairs_kernel body, ~97 % of the pixels): merged matrices per pair (M = K_j R K_i^-1 in fp64, rounded once),
+//          h = d (M [u,v,1]) + K_j t, one approximate reciprocal, two pixels per instruction in packed fp32x2 arithmetic, floor on
+//          the FMA pipe; accepted when the projection is a whole pixel inside the image and one per-pair line in (|d|, h_z)
+//          bounds every forward-error margin below 1 px;
+//   tier 2 (margin_pixel): the same evaluation with PER-PIXEL margins. mvcs_prepare derives a rigorous forward-error bound of
+//          both evaluations against the real-valued result (gamma_n sum |a_i b_i| with n = 32 >= the 12-op chain, at u <= W,
+//          v <= H): |dh_c| <= Bh_c d + Bt_c, which gives a margin on u_j, v_j, z_j; a pixel farther than the margin from
+//          u_j in {0, W}, v_j in {0, H}, z_j = 0 and the z clamp provably takes the same mask decision on both paths;
+//   tier 3 (exact_pixel, ~1 pixel in 10^4 at 504 x 504): the reference's operation order.
+// Sampled values differ by a few ulp between tiers 1-2 and the reference (the tests allow 1e-5 on the per-pair MSE; the counts
+// stay exact).
 #include "common.cuh"
 #include "../../include/videogpa_b200.h"
 #include <math.h>
@@ -30,8 +34,7 @@ namespace vgpa {
 namespace {
 
 constexpr int MV_THREADS = 256;
-constexpr int MV_PIX_PER_THREAD = 4;
-constexpr int MV_PAIR_FLOATS = 64;  // exact path: invK(9) R(9) t(3) Kj(9) | fast path: M(9) Kt(3) Z(3) tz | margins: Au Cu Av Cv Az Cz Ahz Chz
+constexpr int MV_PAIR_FLOATS = 64;  // exact path: invK(9) R(9) t(3) Kj(9) | fast path: M(9) Kt(3) Z(3) tz | margins: Au Cu Av Cv Az Cz Ahz Chz | interior line G1 G2
 constexpr int MV_EXACT_FLOATS = 30;
 constexpr int MV_FAST0 = 32;          // first fast-path constant
 constexpr double MV_GAMMA = 32.0 * 5.9604644775390625e-08;   // 32 * 2^-24
@@ -152,6 +155,19 @@ __global__ void mvcs_prepare_kernel(const float* __restrict__ Kmat, const float*
   f[21] = static_cast<float>((MV_GAMMA * fabs(t[2]) + 1e-30) * up);
   f[22] = static_cast<float>(Bh[2] * up);
   f[23] = static_cast<float>((Bt[2] + 1e-30) * up);
+  // Interior test of mvcs_pairs_kernel: h_z > G1 |d| + G2 must imply (i) margin_pixel's guard h_z > 4 e_z + 2e-8 and (ii) its
+  // u / v margins below 1 px for |u_j| <= W, |v_j| <= H:  (W 1.34 e_z + f16 |d| + f17) rz + W 2^-21 < 0.99 with
+  // rz <= (1 + 2^-22) / h_z. Built from the rounded f[] the margin path itself uses; kappa = 0.95 leaves room for W 2^-21
+  // (W <= 16384), the reciprocal's error and the rounding of the line's own fp32 evaluation.
+  {
+    const double f16 = f[16], f17 = f[17], f18 = f[18], f19 = f[19], f22 = f[22], f23 = f[23], kappa = 0.95;
+    const double s1 = fmax(Wd * 1.34 * f22 + f16, Hd * 1.34 * f22 + f18) / kappa;
+    const double s2 = fmax(Wd * 1.34 * f23 + f17, Hd * 1.34 * f23 + f19) / kappa;
+    double G1 = fmax(s1, 4.0 * f22) * up, G2 = fmax(s2, 4.0 * f23 + 2e-8) * up;
+    if (W > 16384 || H > 16384 || !(G1 == G1) || !(G2 == G2)) { G1 = 0.0; G2 = INFINITY; }   // no pixel passes: margin path only
+    f[24] = static_cast<float>(G1 * up);
+    f[25] = static_cast<float>(G2 * up);
+  }
 }
 
 __device__ __forceinline__ float fetch_zero_pad(const float* __restrict__ img, int x, int y, int W, int H) {
@@ -204,130 +220,178 @@ __device__ __forceinline__ float rcp_fast(float x) {
   return y;
 }
 
-// ONE_ROW: W % 4 == 0, so the 4 consecutive pixels of a thread share their row (the row terms are hoisted) and the depth_i
-// vector load is always in range.
-template <bool ONE_ROW>
-__global__ void __launch_bounds__(MV_THREADS, 3)
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2: two pixels per FMA-pipe instruction; explicit PTX, so the file's
+//      --fmad=false does not touch it)
+__device__ __forceinline__ uint64_t p2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t p2(float c) { return p2(c, c); }
+__device__ __forceinline__ void u2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_rm2(uint64_t a, uint64_t b) {   // round toward -inf
+  uint64_t d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// TIER 2 (and 3): one pixel with per-pixel forward-error margins; a pixel that is not provably decided by the merged-matrix
+// evaluation is handed to `exact_pixel`. Out of line: only pixels that fail the interior test of the kernel below come here
+// (the 1-pixel border ring, projections outside the image, non-positive depth: a few percent of a typical clip).
+__device__ __noinline__ bool margin_pixel(const float* __restrict__ prec, const float* __restrict__ dj, int px, int py, float d,
+                                          int W, int H, float* e2) {
+  float fp[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) fp[k] = __ldg(prec + MV_FAST0 + k);
+  const float Wf = static_cast<float>(W), Hf = static_cast<float>(H);
+  const float half_w = 0.5f * Wf, half_h = 0.5f * Hf;
+  const float u = static_cast<float>(px), v = static_cast<float>(py);
+  const float mx = __fmaf_rn(fp[1], v, fp[2]), my = __fmaf_rn(fp[4], v, fp[5]), mzr = __fmaf_rn(fp[7], v, fp[8]);
+  const float mzz = __fmaf_rn(fp[13], v, fp[14]);
+  // h = d (M [u,v,1]) + K_j t ;  z_j = d (Z [u,v,1]) + t_z
+  const float hx = __fmaf_rn(d, __fmaf_rn(fp[0], u, mx), fp[9]);
+  const float hy = __fmaf_rn(d, __fmaf_rn(fp[3], u, my), fp[10]);
+  const float hz = __fmaf_rn(d, __fmaf_rn(fp[6], u, mzr), fp[11]);
+  const float zj = __fmaf_rn(d, __fmaf_rn(fp[12], u, mzz), fp[15]);
+  const float rz = rcp_fast(fmaxf(hz, 1e-8f));
+  const float uj = hx * rz, vj = hy * rz;
+  // signed distance to the nearest mask boundary (positive inside) against the forward-error margins
+  const float su = half_w - fabsf(uj - half_w), sv = half_h - fabsf(vj - half_h);
+  const float ad = fabsf(d), auj = fabsf(uj), avj = fabsf(vj);
+  const float ez = __fmaf_rn(fp[22], ad, fp[23]), ezs = 1.34f * ez;
+  const float mu = __fmaf_rn(__fmaf_rn(auj, ezs, __fmaf_rn(fp[16], ad, fp[17])), rz, auj * 4.76837158203125e-07f);
+  const float mv = __fmaf_rn(__fmaf_rn(avj, ezs, __fmaf_rn(fp[18], ad, fp[19])), rz, avj * 4.76837158203125e-07f);
+  const float mz = __fmaf_rn(fp[20], ad, fp[21]);
+  // written so that a NaN anywhere selects the exact path; hz > 4 ez + 2e-8 also keeps both paths off the 1e-8 clamp;
+  // the 1e-3 absolute slack covers the rounding of su / sv themselves (|u_j - W/2| is rounded once: <= W 2^-24)
+  const bool clear = (fabsf(su) > mu + 1e-3f) && (fabsf(sv) > mv + 1e-3f) && (fabsf(zj) > mz) && (hz > __fmaf_rn(4.0f, ez, 2e-8f));
+  if (!clear) {                                            // TIER 3: the reference's operation order
+    float spx[MV_EXACT_FLOATS];
+#pragma unroll
+    for (int q = 0; q < MV_EXACT_FLOATS; ++q) spx[q] = __ldg(prec + q);
+    return exact_pixel(spx, dj, px, py, d, W, H, e2);
+  }
+  if (!((su > 0.0f) && (sv > 0.0f) && (zj > 0.0f))) return false;
+  // grid_sample(align_corners=True) maps the normalised coordinate back to u_j, v_j (mvcs.py:85-95; the reference's round
+  // trip adds ~1e-5 px of rounding noise, which this path does not reproduce)
+  const float fx = floorf(uj), fy = floorf(vj);
+  // u_j in [0, W), v_j in [0, H): the base texel is inside; only the +1 neighbours can leave the image (zero padding)
+  const int x0 = min(static_cast<int>(fx), W - 1), y0 = min(static_cast<int>(fy), H - 1);
+  const float tx = uj - fx, ty = vj - fy;
+  const bool okx = x0 + 1 < W, oky = y0 + 1 < H;
+  const float* r0 = dj + (static_cast<long long>(y0) * W + x0);
+  const float v00 = __ldg(r0);
+  const float a01 = okx ? __ldg(r0 + 1) : 0.f, a10 = oky ? __ldg(r0 + W) : 0.f, a11 = (okx && oky) ? __ldg(r0 + W + 1) : 0.f;
+  const float top = __fmaf_rn(tx, a01 - v00, v00), bot = __fmaf_rn(tx, a11 - a10, a10);
+  const float e = __fmaf_rn(ty, bot - top, top) - zj;
+  *e2 = e * e;
+  return true;
+}
+
+// TIER 1: one warp walks one image row; a thread takes the pixel pair (x, x + 32) and evaluates both in packed fp32x2
+// arithmetic. A pixel is finished here when it is provably in the mask by a whole pixel:
+//   * floor(u_j) in [1, W - 2] and floor(v_j) in [1, H - 2] (so u_j, v_j are >= 1 px from every mask boundary, and the four
+//     bilinear taps are inside the image: no zero padding, no clamping), with floor() taken on the FMA pipe by a
+//     round-toward-minus-infinity add of 1.5 * 2^23 (exact for 0 <= x < 2^22; any other input, NaN included, yields an
+//     integer outside the accepted range);
+//   * h_z > G1 |d| + G2, the per-pair line (mvcs_prepare) that bounds BOTH margin_pixel's h_z guard (4 e_z + 2e-8) and
+//     (W 1.34 e_z + Bu |d| + Cu) / 0.95, the numerator of its u / v margin at |u_j| <= W: margin < 0.95 + W 2^-21 < 1 px;
+//   * z_j > Az |d| + Cz, margin_pixel's own z margin (>= 0, so z_j > 0).
+// These imply margin_pixel's `clear && in_mask`, so the pixel takes the same mask decision as the reference, and the sampled
+// value is computed by the same formula as in margin_pixel. Everything else goes to margin_pixel.
+__global__ void __launch_bounds__(MV_THREADS, 2)
 mvcs_pairs_kernel(const float* __restrict__ depths, const float* __restrict__ pairs, int T, int H, int W,
                   int blocks_per_pair, double* __restrict__ part_sum, unsigned int* __restrict__ part_cnt) {
   const int pair_i = blockIdx.y;        // 0..T-2
   const int clip = blockIdx.z;
   const long long pair_idx = static_cast<long long>(clip) * (T - 1) + pair_i;
   const float* prec = pairs + pair_idx * MV_PAIR_FLOATS;
-  float fp[24];                         // fast-path constants in registers
-#pragma unroll
-  for (int k = 0; k < 24; ++k) fp[k] = __ldg(prec + MV_FAST0 + k);
-  const float ez_scale = 1.34f;
+  const float* fpp = prec + MV_FAST0;
   const float* di = depths + (static_cast<long long>(clip) * T + pair_i) * H * W;
   const float* dj = di + static_cast<long long>(H) * W;
-  const int HW = H * W;
-  const float Wf = static_cast<float>(W), Hf = static_cast<float>(H);
-  const float half_w = 0.5f * Wf, half_h = 0.5f * Hf;
-  const float inv_w = 1.0f / Wf;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-pair constants, each duplicated into a register pair
+  const uint64_t m0 = p2(__ldg(fpp + 0)), m3 = p2(__ldg(fpp + 3)), m6 = p2(__ldg(fpp + 6)), z0 = p2(__ldg(fpp + 12));
+  const uint64_t kt0 = p2(__ldg(fpp + 9)), kt1 = p2(__ldg(fpp + 10)), kt2 = p2(__ldg(fpp + 11)), tz = p2(__ldg(fpp + 15));
+  const uint64_t az = p2(__ldg(fpp + 20)), cz = p2(__ldg(fpp + 21)), g1 = p2(__ldg(fpp + 24)), g2 = p2(__ldg(fpp + 25));
+  const float m1 = __ldg(fpp + 1), m2 = __ldg(fpp + 2), m4 = __ldg(fpp + 4), m5 = __ldg(fpp + 5), m7 = __ldg(fpp + 7), m8 = __ldg(fpp + 8);
+  const float z1 = __ldg(fpp + 13), z2 = __ldg(fpp + 14);
+  const uint64_t magic = p2(12582912.0f);                       // 1.5 * 2^23: ulp 1, so a round-down add leaves floor(x)
+  const unsigned int xr = static_cast<unsigned int>(W - 2), yr = static_cast<unsigned int>(H - 2), Wu = static_cast<unsigned int>(W);
   double acc = 0.0;
   unsigned int cnt = 0;
-  const int stride = blocks_per_pair * MV_THREADS * MV_PIX_PER_THREAD;
-  for (int base = (blockIdx.x * MV_THREADS + threadIdx.x) * MV_PIX_PER_THREAD; base < HW; base += stride) {
-    float d0, d1, d2, d3;
-    if (ONE_ROW) {
-      const float4 q = *reinterpret_cast<const float4*>(di + base);
-      d0 = q.x; d1 = q.y; d2 = q.z; d3 = q.w;
-    } else {
-      d0 = di[base];
-      d1 = (base + 1 < HW) ? di[base + 1] : 0.f;
-      d2 = (base + 2 < HW) ? di[base + 2] : 0.f;
-      d3 = (base + 3 < HW) ? di[base + 3] : 0.f;
-    }
-    const float dd[MV_PIX_PER_THREAD] = {d0, d1, d2, d3};
-    // row / column of the first pixel without an integer division (exact below 2^24 pixels; checked by the host wrapper)
-    int py0 = __float2int_rz(__int2float_rz(base) * inv_w);
-    int px0 = base - py0 * W;
-    if (px0 >= W) { px0 -= W; ++py0; }
-    if (px0 < 0) { px0 += W; --py0; }
-    const float u0 = static_cast<float>(px0), v0 = static_cast<float>(py0);
-    // row terms of M [u,v,1] and Z [u,v,1]
-    const float rx = __fmaf_rn(fp[1], v0, fp[2]), ry = __fmaf_rn(fp[4], v0, fp[5]), rzr = __fmaf_rn(fp[7], v0, fp[8]);
-    const float rzz = __fmaf_rn(fp[13], v0, fp[14]);
-    // ---- phase 1: projection, mask and sample coordinates of the 4 pixels (no loads, no branches)
-    float zj[MV_PIX_PER_THREAD], tx[MV_PIX_PER_THREAD], ty[MV_PIX_PER_THREAD];
-    int off[MV_PIX_PER_THREAD];
-    bool take[MV_PIX_PER_THREAD], redo[MV_PIX_PER_THREAD], okx[MV_PIX_PER_THREAD], oky[MV_PIX_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < MV_PIX_PER_THREAD; ++k) {
-      float u = u0 + static_cast<float>(k), mx = rx, my = ry, mzr = rzr, mzz = rzz;
-      bool live = true;
-      if (!ONE_ROW) {
-        int px = px0 + k, py = py0;
-        if (px >= W) { px -= W; ++py; }
-        live = base + k < HW;
-        u = static_cast<float>(px);
-        const float v = static_cast<float>(py);
-        mx = __fmaf_rn(fp[1], v, fp[2]); my = __fmaf_rn(fp[4], v, fp[5]); mzr = __fmaf_rn(fp[7], v, fp[8]); mzz = __fmaf_rn(fp[13], v, fp[14]);
-      }
-      const float d = dd[k];
+  for (int row = blockIdx.x * (MV_THREADS / 32) + warp; row < H; row += blocks_per_pair * (MV_THREADS / 32)) {
+    const float v = static_cast<float>(row);
+    const uint64_t rx = p2(__fmaf_rn(m1, v, m2)), ry = p2(__fmaf_rn(m4, v, m5)), rzr = p2(__fmaf_rn(m7, v, m8));
+    const uint64_t rzz = p2(__fmaf_rn(z1, v, z2));
+    const float* drow = di + static_cast<long long>(row) * W;
+    float part_a = 0.f, part_b = 0.f;                           // fp32 sums of this thread's squared errors in this row
+#pragma unroll 2
+    for (int x = lane; x < W; x += 64) {
+      const bool live_b = x + 32 < W;
+      const float da = __ldg(drow + x);
+      const float db = live_b ? __ldg(drow + x + 32) : 0.f;
+      const float ua = static_cast<float>(x);
+      const uint64_t uu = p2(ua, ua + 32.0f), dd = p2(da, db);
       // h = d (M [u,v,1]) + K_j t ;  z_j = d (Z [u,v,1]) + t_z
-      const float hx = __fmaf_rn(d, __fmaf_rn(fp[0], u, mx), fp[9]);
-      const float hy = __fmaf_rn(d, __fmaf_rn(fp[3], u, my), fp[10]);
-      const float hz = __fmaf_rn(d, __fmaf_rn(fp[6], u, mzr), fp[11]);
-      zj[k] = __fmaf_rn(d, __fmaf_rn(fp[12], u, mzz), fp[15]);
-      const float rz = rcp_fast(fmaxf(hz, 1e-8f));
-      const float uj = hx * rz, vj = hy * rz;
-      // signed distance to the nearest mask boundary (positive inside) against the forward-error margins
-      const float su = half_w - fabsf(uj - half_w), sv = half_h - fabsf(vj - half_h);
-      const float ad = fabsf(d), auj = fabsf(uj), avj = fabsf(vj);
-      const float ez = __fmaf_rn(fp[22], ad, fp[23]), ezs = ez_scale * ez;
-      const float mu = __fmaf_rn(__fmaf_rn(auj, ezs, __fmaf_rn(fp[16], ad, fp[17])), rz, auj * 4.76837158203125e-07f);
-      const float mv = __fmaf_rn(__fmaf_rn(avj, ezs, __fmaf_rn(fp[18], ad, fp[19])), rz, avj * 4.76837158203125e-07f);
-      const float mz = __fmaf_rn(fp[20], ad, fp[21]);
-      // written so that a NaN anywhere selects the exact path; hz > 4 ez + 2e-8 also keeps both paths off the 1e-8 clamp;
-      // the 1e-3 absolute slack covers the rounding of su / sv themselves (|u_j - W/2| is rounded once: <= W 2^-24)
-      const bool clear = (fabsf(su) > mu + 1e-3f) && (fabsf(sv) > mv + 1e-3f) && (fabsf(zj[k]) > mz) && (hz > __fmaf_rn(4.0f, ez, 2e-8f));
-      const bool in_mask = (su > 0.0f) && (sv > 0.0f) && (zj[k] > 0.0f);
-      take[k] = live && clear && in_mask;
-      redo[k] = live && !clear;
-      // grid_sample(align_corners=True) maps the normalised coordinate back to u_j, v_j (mvcs.py:85-95; the reference's round
-      // trip adds ~1e-5 px of rounding noise, which this path does not reproduce)
-      const float ix = take[k] ? uj : 0.0f, iy = take[k] ? vj : 0.0f;
-      const float fx = floorf(ix), fy = floorf(iy);
-      // u_j in [0, W), v_j in [0, H): the base texel is inside; only the +1 neighbours can leave the image (zero padding)
-      const int x0 = min(static_cast<int>(fx), W - 1), y0 = min(static_cast<int>(fy), H - 1);
-      tx[k] = ix - fx; ty[k] = iy - fy;
-      okx[k] = x0 + 1 < W; oky[k] = y0 + 1 < H;
-      off[k] = y0 * W + x0;
-    }
-    // ---- phase 2: the 16 gathers of depth_j, all addresses valid (clamped), issued together
-    float v00[MV_PIX_PER_THREAD], v01[MV_PIX_PER_THREAD], v10[MV_PIX_PER_THREAD], v11[MV_PIX_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < MV_PIX_PER_THREAD; ++k) {
-      const int ox = okx[k] ? 1 : 0, oy = oky[k] ? W : 0;
-      const float* r0 = dj + off[k];
-      v00[k] = __ldg(r0); v01[k] = __ldg(r0 + ox); v10[k] = __ldg(r0 + oy); v11[k] = __ldg(r0 + oy + ox);
-    }
-    // ---- phase 3: bilinear sample, squared error
-    float part = 0.f;                                      // fp32 sum of this thread's 4 squared errors, added in fp64 below
-#pragma unroll
-    for (int k = 0; k < MV_PIX_PER_THREAD; ++k) {
-      const float a01 = okx[k] ? v01[k] : 0.f, a10 = oky[k] ? v10[k] : 0.f, a11 = (okx[k] && oky[k]) ? v11[k] : 0.f;
-      const float top = __fmaf_rn(tx[k], a01 - v00[k], v00[k]), bot = __fmaf_rn(tx[k], a11 - a10, a10);
-      const float e = __fmaf_rn(ty[k], bot - top, top) - zj[k];
-      part = take[k] ? __fmaf_rn(e, e, part) : part;
-      cnt += take[k] ? 1u : 0u;
-    }
-    acc += static_cast<double>(part);
-    // ---- phase 4 (rare): pixels too close to a mask boundary are re-evaluated in the reference's operation order
-    if (redo[0] || redo[1] || redo[2] || redo[3]) {
-      float spx[MV_EXACT_FLOATS];
-#pragma unroll
-      for (int q = 0; q < MV_EXACT_FLOATS; ++q) spx[q] = __ldg(prec + q);
-#pragma unroll
-      for (int k = 0; k < MV_PIX_PER_THREAD; ++k) {
-        if (!redo[k]) continue;
-        int py = py0, px = px0 + k;
-        if (px >= W) { px -= W; ++py; }
+      const uint64_t hx = fma2(dd, fma2(m0, uu, rx), kt0);
+      const uint64_t hy = fma2(dd, fma2(m3, uu, ry), kt1);
+      const uint64_t hz = fma2(dd, fma2(m6, uu, rzr), kt2);
+      const uint64_t zj = fma2(dd, fma2(z0, uu, rzz), tz);
+      float hza, hzb;
+      u2(hz, hza, hzb);
+      const uint64_t rz = p2(rcp_fast(fmaxf(hza, 1e-8f)), rcp_fast(fmaxf(hzb, 1e-8f)));
+      const uint64_t uj = mul2(hx, rz), vj = mul2(hy, rz);
+      const uint64_t tu = add_rm2(uj, magic), tv = add_rm2(vj, magic);
+      const uint64_t tx = sub2(uj, sub2(tu, magic)), ty = sub2(vj, sub2(tv, magic));
+      const uint64_t ad = dd & 0x7fffffff7fffffffull;
+      const uint64_t gz = fma2(g1, ad, g2), mz = fma2(az, ad, cz);
+      float tua, tub, tva, tvb, gza, gzb, mza, mzb, zja, zjb;
+      u2(tu, tua, tub); u2(tv, tva, tvb); u2(gz, gza, gzb); u2(mz, mza, mzb); u2(zj, zja, zjb);
+      const int x0a = __float_as_int(tua) - 0x4B400000, x0b = __float_as_int(tub) - 0x4B400000;
+      const int y0a = __float_as_int(tva) - 0x4B400000, y0b = __float_as_int(tvb) - 0x4B400000;
+      const bool in_a = (static_cast<unsigned int>(x0a - 1) < xr) && (static_cast<unsigned int>(y0a - 1) < yr) && (hza > gza) && (zja > mza);
+      const bool in_b = live_b && (static_cast<unsigned int>(x0b - 1) < xr) && (static_cast<unsigned int>(y0b - 1) < yr) && (hzb > gzb) &&
+                        (zjb > mzb);
+      // the 8 gathers of depth_j: addresses forced valid (offset 0) for pixels that leave this path
+      // (unsigned 32-bit element offsets: one IMAD.WIDE.U32 per row pointer)
+      const unsigned int oa = in_a ? static_cast<unsigned int>(y0a * W + x0a) : 0u;
+      const unsigned int ob = in_b ? static_cast<unsigned int>(y0b * W + x0b) : 0u;
+      const float* ra0 = dj + oa;
+      const float* ra1 = dj + (oa + Wu);
+      const float* rb0 = dj + ob;
+      const float* rb1 = dj + (ob + Wu);
+      const float a00 = __ldg(ra0), a01 = __ldg(ra0 + 1), a10 = __ldg(ra1), a11 = __ldg(ra1 + 1);
+      const float b00 = __ldg(rb0), b01 = __ldg(rb0 + 1), b10 = __ldg(rb1), b11 = __ldg(rb1 + 1);
+      const uint64_t v00 = p2(a00, b00), v10 = p2(a10, b10);
+      const uint64_t top = fma2(tx, sub2(p2(a01, b01), v00), v00), bot = fma2(tx, sub2(p2(a11, b11), v10), v10);
+      float ea, eb;
+      u2(sub2(fma2(ty, sub2(bot, top), top), zj), ea, eb);
+      part_a = in_a ? __fmaf_rn(ea, ea, part_a) : part_a;
+      part_b = in_b ? __fmaf_rn(eb, eb, part_b) : part_b;
+      cnt += (in_a ? 1u : 0u) + (in_b ? 1u : 0u);
+      if (!in_a || (live_b && !in_b)) {                         // border ring, outside the image, z <= 0, NaN: margin / exact path
         float e2;
-        if (exact_pixel(spx, dj, px, py, dd[k], W, H, &e2)) { acc += static_cast<double>(e2); ++cnt; }
+        if (!in_a && margin_pixel(prec, dj, x, row, da, W, H, &e2)) { acc += static_cast<double>(e2); ++cnt; }
+        if (live_b && !in_b && margin_pixel(prec, dj, x + 32, row, db, W, H, &e2)) { acc += static_cast<double>(e2); ++cnt; }
       }
     }
+    acc += static_cast<double>(part_a) + static_cast<double>(part_b);
   }
   // block reduction in a fixed order
   __shared__ double s_sum[MV_THREADS / 32];
@@ -335,7 +399,6 @@ mvcs_pairs_kernel(const float* __restrict__ depths, const float* __restrict__ pa
   acc = warp_sum_d(acc);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { s_sum[warp] = acc; s_cnt[warp] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -376,9 +439,9 @@ extern "C" size_t vgpa_mvcs_workspace_bytes(int n_clips, int T, int H, int W) {
 }
 
 extern "C" int vgpa_mvcs_blocks_per_pair(int n_clips, int T, int H, int W) {
-  const long long hw = static_cast<long long>(H) * W;
-  const long long per_block = vgpa::MV_THREADS * vgpa::MV_PIX_PER_THREAD;
-  long long need = (hw + per_block - 1) / per_block;
+  (void)W;
+  const long long rows_per_pass = vgpa::MV_THREADS / 32;           // one warp walks one image row at a time
+  long long need = (H + rows_per_pass - 1) / rows_per_pass;
   // enough blocks to fill the machine (148 SMs x 8 resident CTAs) without shrinking below one pass per block
   const long long n_pairs = static_cast<long long>(n_clips > 0 ? n_clips : 1) * (T > 1 ? T - 1 : 1);
   long long want = (148LL * 8 + n_pairs - 1) / n_pairs;
@@ -416,8 +479,7 @@ extern "C" int vgpa_mvcs_batch(const float* d_depths, const float* d_intrinsics,
   VGPA_CHECK(n_clips <= 65535 && T - 1 <= 65535, "vgpa_mvcs_batch: too many clips per launch (%d)", n_clips);
   VGPA_CHECK(static_cast<long long>(H) * W < (1LL << 24) && H >= 2 && W >= 2, "vgpa_mvcs_batch: frames must be between 2x2 and 2^24 pixels (H=%d W=%d)", H, W);
   dim3 grid(bpp, T - 1, n_clips);
-  if ((W & 3) == 0) mvcs_pairs_kernel<true><<<grid, MV_THREADS, 0, s>>>(d_depths, pairs, T, H, W, bpp, part_sum, part_cnt);
-  else mvcs_pairs_kernel<false><<<grid, MV_THREADS, 0, s>>>(d_depths, pairs, T, H, W, bpp, part_sum, part_cnt);
+  mvcs_pairs_kernel<<<grid, MV_THREADS, 0, s>>>(d_depths, pairs, T, H, W, bpp, part_sum, part_cnt);
   VGPA_LAUNCH_CHECK("mvcs_pairs_kernel");
   mvcs_finalize_kernel<<<(n_clips + 127) / 128, 128, 0, s>>>(part_sum, part_cnt, n_clips, T, bpp, d_pair_mse,
                                                             reinterpret_cast<long long*>(d_pair_cnt), d_scores);

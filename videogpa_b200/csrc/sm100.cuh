@@ -178,6 +178,26 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUte
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same loads with an L2 eviction-priority policy (createpolicy encodings: evict_first for data streamed once, evict_last
+// for the operand every CTA re-reads, normal = no preference).
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                           uint16_t cta_mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+      "[%0], [%1, {%4, %5}], [%2], %3, %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 // tcgen05.commit that arrives on the mbarrier at this smem offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
