@@ -446,19 +446,25 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
   ep.rope_cos = a->rope_cos; ep.rope_sin = a->rope_sin;
   ep.model_dim = a->model_dim;
   ep.alpha = a->alpha;
-  // development knobs (read once): raster group height and L2 policies
-  static int k_group = -1, k_stream = -1, k_hints = -1;
-  if (k_group < 0) {
-    const char* e = getenv("VGPA_GEMM_GROUP_M");  k_group = e ? atoi(e) : GROUP_M_DEFAULT;
-    e = getenv("VGPA_GEMM_STREAM_OUT");           k_stream = e ? atoi(e) : 0;
-    e = getenv("VGPA_GEMM_HINTS");                k_hints = e ? atoi(e) : 0;
-    if (k_group < 1) k_group = GROUP_M_DEFAULT;
+  // Rasterisation and L2 policy. A raster group is `group_m` M tiles (tile pairs with a cluster) swept across all of N: the A rows of
+  // the group are what must survive in L2 while W and the output stream through. Measured on the DiT shapes (profiles/r02_gemm_l2.md):
+  // for K = 3072 a 24-pair group (6144 rows, 38 MB) with evict-last A loads and streaming (evict-first) output stores reads 843 MB from
+  // DRAM for FF1 against 908 MB with 16 / no hints and is 1.5-2 % faster; 32 pairs (50 MB) no longer survives (1.42 GB). With K = 12288
+  // (FF2) a group already exceeds L2 and the hints cost 3 %: plain loads, 16. VGPA_GEMM_GROUP_M / _STREAM_OUT / _HINTS override (dev).
+  static int k_group = -2, k_stream = -2, k_hints = -2;
+  if (k_group == -2) {
+    const char* e = getenv("VGPA_GEMM_GROUP_M");  k_group = e ? atoi(e) : -1;
+    e = getenv("VGPA_GEMM_STREAM_OUT");           k_stream = e ? atoi(e) : -1;
+    e = getenv("VGPA_GEMM_HINTS");                k_hints = e ? atoi(e) : -1;
   }
-  ep.group_m = k_group;
+  const bool short_k = a->K <= 4096;
+  const int hints = k_hints >= 0 ? k_hints : (short_k ? 1 : 0);
+  ep.group_m = k_group >= 1 ? k_group : (short_k ? 24 : GROUP_M_DEFAULT);
   // in-place epilogues re-read what they store (residual / accumulate): never stream those
-  ep.stream_out = (k_stream && a->epilogue != VGPA_EPI_GATE_RES && a->epilogue != VGPA_EPI_ACCUM && a->epilogue != VGPA_EPI_GATE_RES_F32) ? 1 : 0;
-  ep.hint_a = (k_hints & 1) ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;     // the A group is what a raster group re-reads across N
-  ep.hint_w = (k_hints & 2) ? ptx::L2_EVICT_FIRST : ((k_hints & 4) ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL);
+  const bool in_place = a->epilogue == VGPA_EPI_GATE_RES || a->epilogue == VGPA_EPI_ACCUM || a->epilogue == VGPA_EPI_GATE_RES_F32;
+  ep.stream_out = ((k_stream >= 0 ? k_stream : (short_k ? 1 : 0)) && !in_place) ? 1 : 0;
+  ep.hint_a = (hints & 1) ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
+  ep.hint_w = (hints & 2) ? ptx::L2_EVICT_FIRST : ((hints & 4) ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL);
   if (a->epilogue == VGPA_EPI_QKV) {
     VGPA_CHECK(a->model_dim > 0 && a->model_dim % 64 == 0 && a->N == 3 * a->model_dim,
                "vgpa_linear_bf16: QKV epilogue needs N == 3*model_dim (N=%d model_dim=%d)", a->N, a->model_dim);

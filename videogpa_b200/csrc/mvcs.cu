@@ -314,53 +314,57 @@ __device__ __noinline__ bool margin_pixel(const float* __restrict__ prec, const 
 //   * z_j > Az |d| + Cz, margin_pixel's own z margin (>= 0, so z_j > 0).
 // These imply margin_pixel's `clear && in_mask`, so the pixel takes the same mask decision as the reference, and the sampled
 // value is computed by the same formula as in margin_pixel. Everything else goes to margin_pixel.
-__global__ void __launch_bounds__(MV_THREADS, 2)
+__global__ void __launch_bounds__(MV_THREADS, 4)
 mvcs_pairs_kernel(const float* __restrict__ depths, const float* __restrict__ pairs, int T, int H, int W,
                   int blocks_per_pair, double* __restrict__ part_sum, unsigned int* __restrict__ part_cnt) {
   const int pair_i = blockIdx.y;        // 0..T-2
   const int clip = blockIdx.z;
   const long long pair_idx = static_cast<long long>(clip) * (T - 1) + pair_i;
   const float* prec = pairs + pair_idx * MV_PAIR_FLOATS;
-  const float* fpp = prec + MV_FAST0;
+  __shared__ float s_fp[32];            // the pair's fast-path constants; the row-start ones are re-read from here per row
+  if (threadIdx.x < 32) s_fp[threadIdx.x] = __ldg(prec + MV_FAST0 + threadIdx.x);
+  __syncthreads();
   const float* di = depths + (static_cast<long long>(clip) * T + pair_i) * H * W;
   const float* dj = di + static_cast<long long>(H) * W;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // per-pair constants, each duplicated into a register pair
-  const uint64_t m0 = p2(__ldg(fpp + 0)), m3 = p2(__ldg(fpp + 3)), m6 = p2(__ldg(fpp + 6)), z0 = p2(__ldg(fpp + 12));
-  const uint64_t kt0 = p2(__ldg(fpp + 9)), kt1 = p2(__ldg(fpp + 10)), kt2 = p2(__ldg(fpp + 11)), tz = p2(__ldg(fpp + 15));
-  const uint64_t az = p2(__ldg(fpp + 20)), cz = p2(__ldg(fpp + 21)), g1 = p2(__ldg(fpp + 24)), g2 = p2(__ldg(fpp + 25));
-  const float m1 = __ldg(fpp + 1), m2 = __ldg(fpp + 2), m4 = __ldg(fpp + 4), m5 = __ldg(fpp + 5), m7 = __ldg(fpp + 7), m8 = __ldg(fpp + 8);
-  const float z1 = __ldg(fpp + 13), z2 = __ldg(fpp + 14);
-  const uint64_t magic = p2(12582912.0f);                       // 1.5 * 2^23: ulp 1, so a round-down add leaves floor(x)
+  // constants of the inner loop (scalar registers: the packed instructions broadcast a 32-bit operand to both halves)
+  const float m0 = s_fp[0], m3 = s_fp[3], m6 = s_fp[6], z0 = s_fp[12];
+  const float kt0 = s_fp[9], kt1 = s_fp[10], kt2 = s_fp[11], tz = s_fp[15];
+  const float az = s_fp[20], cz = s_fp[21], g1 = s_fp[24], g2 = s_fp[25];
   const unsigned int xr = static_cast<unsigned int>(W - 2), yr = static_cast<unsigned int>(H - 2), Wu = static_cast<unsigned int>(W);
   double acc = 0.0;
   unsigned int cnt = 0;
   for (int row = blockIdx.x * (MV_THREADS / 32) + warp; row < H; row += blocks_per_pair * (MV_THREADS / 32)) {
     const float v = static_cast<float>(row);
-    const uint64_t rx = p2(__fmaf_rn(m1, v, m2)), ry = p2(__fmaf_rn(m4, v, m5)), rzr = p2(__fmaf_rn(m7, v, m8));
-    const uint64_t rzz = p2(__fmaf_rn(z1, v, z2));
+    const float rx = __fmaf_rn(s_fp[1], v, s_fp[2]), ry = __fmaf_rn(s_fp[4], v, s_fp[5]), rzr = __fmaf_rn(s_fp[7], v, s_fp[8]);
+    const float rzz = __fmaf_rn(s_fp[13], v, s_fp[14]);
     const float* drow = di + static_cast<long long>(row) * W;
     float part_a = 0.f, part_b = 0.f;                           // fp32 sums of this thread's squared errors in this row
-#pragma unroll 2
+    // depth_i of the NEXT pixel pair is requested before the current pair's arithmetic: the HBM latency of the streamed
+    // operand overlaps the L2 latency of the gathers instead of adding to it
+    float da = (lane < W) ? __ldg(drow + lane) : 0.f;
+    float db = (lane + 32 < W) ? __ldg(drow + lane + 32) : 0.f;
+#pragma unroll 1
     for (int x = lane; x < W; x += 64) {
       const bool live_b = x + 32 < W;
-      const float da = __ldg(drow + x);
-      const float db = live_b ? __ldg(drow + x + 32) : 0.f;
+      const float da_n = (x + 64 < W) ? __ldg(drow + x + 64) : 0.f;
+      const float db_n = (x + 96 < W) ? __ldg(drow + x + 96) : 0.f;
       const float ua = static_cast<float>(x);
       const uint64_t uu = p2(ua, ua + 32.0f), dd = p2(da, db);
       // h = d (M [u,v,1]) + K_j t ;  z_j = d (Z [u,v,1]) + t_z
-      const uint64_t hx = fma2(dd, fma2(m0, uu, rx), kt0);
-      const uint64_t hy = fma2(dd, fma2(m3, uu, ry), kt1);
-      const uint64_t hz = fma2(dd, fma2(m6, uu, rzr), kt2);
-      const uint64_t zj = fma2(dd, fma2(z0, uu, rzz), tz);
+      const uint64_t hx = fma2(dd, fma2(p2(m0), uu, p2(rx)), p2(kt0));
+      const uint64_t hy = fma2(dd, fma2(p2(m3), uu, p2(ry)), p2(kt1));
+      const uint64_t hz = fma2(dd, fma2(p2(m6), uu, p2(rzr)), p2(kt2));
+      const uint64_t zj = fma2(dd, fma2(p2(z0), uu, p2(rzz)), p2(tz));
       float hza, hzb;
       u2(hz, hza, hzb);
       const uint64_t rz = p2(rcp_fast(fmaxf(hza, 1e-8f)), rcp_fast(fmaxf(hzb, 1e-8f)));
       const uint64_t uj = mul2(hx, rz), vj = mul2(hy, rz);
+      const uint64_t magic = p2(12582912.0f);                   // 1.5 * 2^23: ulp 1, so a round-down add leaves floor(x)
       const uint64_t tu = add_rm2(uj, magic), tv = add_rm2(vj, magic);
       const uint64_t tx = sub2(uj, sub2(tu, magic)), ty = sub2(vj, sub2(tv, magic));
       const uint64_t ad = dd & 0x7fffffff7fffffffull;
-      const uint64_t gz = fma2(g1, ad, g2), mz = fma2(az, ad, cz);
+      const uint64_t gz = fma2(p2(g1), ad, p2(g2)), mz = fma2(p2(az), ad, p2(cz));
       float tua, tub, tva, tvb, gza, gzb, mza, mzb, zja, zjb;
       u2(tu, tua, tub); u2(tv, tva, tvb); u2(gz, gza, gzb); u2(mz, mza, mzb); u2(zj, zja, zjb);
       const int x0a = __float_as_int(tua) - 0x4B400000, x0b = __float_as_int(tub) - 0x4B400000;
@@ -390,6 +394,7 @@ mvcs_pairs_kernel(const float* __restrict__ depths, const float* __restrict__ pa
         if (!in_a && margin_pixel(prec, dj, x, row, da, W, H, &e2)) { acc += static_cast<double>(e2); ++cnt; }
         if (live_b && !in_b && margin_pixel(prec, dj, x + 32, row, db, W, H, &e2)) { acc += static_cast<double>(e2); ++cnt; }
       }
+      da = da_n; db = db_n;
     }
     acc += static_cast<double>(part_a) + static_cast<double>(part_b);
   }
