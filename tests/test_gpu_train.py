@@ -241,7 +241,7 @@ def test_dpo_training_step_gradients_vs_oracle_autograd(lib):
     assert names[0] == "base_model.model.transformer_blocks.0.attn1.to_q.lora_A.weight" and len(names) == 16
 
 
-@pytest.mark.parametrize("variant", ["t2v", "i2v_posemb"])
+@pytest.mark.parametrize("variant", ["t2v", "i2v_posemb", "1.5_temporal_patch"])
 def test_training_forward_matches_inference_with_zero_lora(lib, variant):
     """With B = 0 (PEFT's initial state) the differentiable forward equals the inference transformer called without rotary
     embeddings up to the different rounding points of the unfused training path (<= 2e-2 of the max)."""
@@ -253,11 +253,15 @@ def test_training_forward_matches_inference_with_zero_lora(lib, variant):
     if variant == "i2v_posemb":                               # train/CogVideoX-I2V-5B: in_channels 32, learned positional embedding
         kw.update(in_channels=32, use_learned_positional_embeddings=True)
         cin = 32
+    frames = 3
+    if variant == "1.5_temporal_patch":                       # train/CogVideoX1.5-5B: patch_size_t 2 (Linear patch embed, even frame count)
+        kw.update(patch_size_t=2)
+        frames = 4
     sd = {k: v.to(BF).float() for k, v in O.random_state_dict(O.DiTConfig(**kw), seed=8, randomize_norms=True, std=0.05).items()}
     base = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
     pol = LoRATrainableTransformer(base)
     g = torch.Generator().manual_seed(4)
-    x = torch.randn(4, 3, cin, 16, 24, generator=g).cuda()
+    x = torch.randn(4, frames, cin, 16, 24, generator=g).cuda()
     e = torch.randn(4, 18, 256, generator=g).to(BF).cuda()
     t = torch.tensor([5, 300, 700, 999]).cuda()
     with torch.no_grad():
@@ -382,3 +386,70 @@ def test_i2v_training_step_with_image_condition(lib):
 
 def _bf16(sd):
     return {k: v.to(BF).float() for k, v in sd.items()}
+
+
+def test_cogvideox1_5_training_step_trims_and_matches_oracle(lib):
+    """train/CogVideoX1.5-5B/03_train.py:134-157 on a temporal-patch model: odd latent sizes are trimmed to even F / H / W, the
+    loss of training_step equals the oracle's (fp32 CPU forward of the same 2-block model, LoRA at its PEFT initial state so
+    policy == reference and the loss is log 2 exactly), and backward reaches the LoRA factors with finite, non-zero dA."""
+    from oracle import dit_torch as O
+    from videogpa_b200.train_dit import LoRATrainableTransformer
+    from videogpa_b200.train_step import DPOSharedStep
+    from videogpa_b200.transformer import CogVideoXTransformer3D, TransformerConfig
+    kw = dict(num_attention_heads=4, num_layers=2, text_embed_dim=256, sample_width=24, sample_height=16, sample_frames=9, max_text_seq_length=18,
+              patch_size_t=2)
+    ocfg = O.DiTConfig(**kw)
+    sd = {k: v.to(BF).float() for k, v in O.random_state_dict(ocfg, seed=9, randomize_norms=True, std=0.05).items()}
+    base = CogVideoXTransformer3D(TransformerConfig(**kw), sd, device="cuda")
+    pol = LoRATrainableTransformer(base, r=64, lora_alpha=128.0, seed=3)
+    g = torch.Generator().manual_seed(5)
+    Bsz, C, Fr, H, W, St = 1, 16, 5, 17, 25, 18                   # odd everywhere: trimmed to 4 x 16 x 24
+    batch = {"x_win": torch.randn(Bsz, C, Fr, H, W, generator=g), "x_lose": torch.randn(Bsz, C, Fr, H, W, generator=g),
+             "prompt_emb": torch.randn(Bsz, St, 256, generator=g).to(BF)}
+    t = torch.tensor([640])
+    noise = torch.randn(Bsz, Fr, C, H, W, generator=g)
+    step = DPOSharedStep(base, None, beta=1.0, trainable=pol)
+    loss = step.training_step(batch, timesteps=t.cuda(), noise=noise.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - math.log(2.0)) < 2e-3                # B = 0: policy == reference up to the training path's rounding points
+    # the prediction itself against the oracle on the trimmed input
+    ac = O.cogvideox_alphas_cumprod()
+    xw = batch["x_win"].permute(0, 2, 1, 3, 4)[:, :4, :, :16, :24]
+    nz = noise[:, :4, :, :16, :24]
+    want = O.transformer_forward(sd, ocfg, O.add_noise(ac, xw, nz, t.numpy()), batch["prompt_emb"].float(), t, None)
+    with torch.no_grad():
+        got = pol(O.add_noise(ac, xw, nz, t.numpy()).cuda(), batch["prompt_emb"].cuda(), t.cuda())
+    assert got.shape == want.shape == (1, 4, 16, 16, 24) and relmax(got.cpu(), want) < 3e-2
+    grads = [p.grad for n, p in pol.named_parameters() if "lora_B" in n]
+    assert all(gr is not None and torch.isfinite(gr).all() for gr in grads) and any(float(gr.abs().max()) > 0 for gr in grads)
+
+
+def test_train_cli_1_5_synthetic(lib, tmp_path, capsys):
+    """`python -m videogpa_b200.train.cogvideox1_5_5b --synthetic 1`: the 1.5 defaults (max_steps 1500, no VAE switches) and one
+    optimizer step on a 1-block temporal-patch model fed by a dataset with odd latent sizes."""
+    import json
+    import yaml
+    from videogpa_b200.train import cogvideox1_5_5b as cli
+    assert cli.DEFAULT_CONFIG["max_steps"] == 1500 and cli.DEFAULT_CONFIG["model_path"] == "THUDM/CogVideoX1.5-5B"
+    assert "enable_tiling" not in cli.DEFAULT_CONFIG
+    root = tmp_path / "data"
+    (root / "lat").mkdir(parents=True)
+    g = torch.Generator().manual_seed(0)
+    groups = []
+    for gi in range(3):
+        vids = []
+        for vi, score in enumerate((0.1, 0.9)):
+            lp = f"lat/g{gi}_v{vi}.pt"
+            torch.save(torch.randn(16, 3, 9, 13, generator=g), str(root / lp))
+            cp = f"lat/g{gi}_v{vi}_cond.pt"
+            torch.save({"encoder_hidden_states": torch.randn(18, 4096, generator=g).to(BF)}, str(root / cp))
+            vids.append({"video_path": f"v{gi}_{vi}.mp4", "consistency_score": score, "motion_norm": 1.0, "latent_path": lp, "condition_path": cp})
+        groups.append({"group_id": f"g{gi}", "text_prompt": "p", "videos": vids})
+    (root / "meta.json").write_text(json.dumps({"groups": groups}))
+    cfgf = tmp_path / "c.yaml"
+    cfgf.write_text(yaml.safe_dump({"training": {"metadata_path": str(root / "meta.json"), "output_dir": str(tmp_path / "out"), "max_steps": 1,
+                                                 "accumulate_grad_batches": 1, "warmup_steps": 1, "devices": [0], "log_every_n_steps": 1}}))
+    res = cli.main(["--config", str(cfgf), "--base_path", str(root), "--synthetic", "1"])
+    assert res["steps"] == 1 and math.isfinite(res["last_loss"])
+    assert (tmp_path / "out" / "final_lora" / "adapter_model.safetensors").exists()

@@ -182,7 +182,9 @@ def main_train(config: dict, synthetic_layers: int = 0) -> dict:
     val_loader = DataLoader(val_ds, batch_size=1, shuffle=False, collate_fn=collate_fn) if len(val_ds) else None
 
     if synthetic_layers:
-        cfg = TransformerConfig.cogvideox_5b_i2v() if config.get("synthetic_variant") == "i2v" else TransformerConfig.cogvideox_5b()
+        variant = config.get("synthetic_variant")
+        cfg = (TransformerConfig.cogvideox_5b_i2v() if variant == "i2v" else
+               TransformerConfig.cogvideox1_5_5b() if variant == "1.5" else TransformerConfig.cogvideox_5b())
         cfg.num_layers = synthetic_layers
         transformer = CogVideoXTransformer3D.random_init(cfg, seed=1234, device=device)
     else:

@@ -338,9 +338,10 @@ class LoRATrainableTransformer:
         autograd graph reaching the LoRA factors. No rotary embedding, as in the reference's training call."""
         t = self.base
         c = self.config
-        if (c.patch_size_t or 1) != 1:
-            raise RuntimeError("the training forward covers the CogVideoX-5B T2V / I2V layouts (no temporal patching)")
+        pt = c.patch_size_t or 1                                   # CogVideoX1.5 (train/CogVideoX1.5-5B/03_train.py): temporal patches of 2
         B, Fr, Cc, H, W = hidden_states.shape
+        if Fr % pt != 0:
+            raise RuntimeError(f"the number of latent frames ({Fr}) must be a multiple of patch_size_t ({pt}); the training step trims it")
         p, D, heads = c.patch_size, c.inner_dim, c.num_attention_heads
         dev = self.device
         with torch.no_grad():
@@ -348,7 +349,7 @@ class LoRATrainableTransformer:
             enc_in = encoder_hidden_states.to(device=dev, dtype=BF16).contiguous()
             St = enc_in.shape[1]
             hw = (H // p) * (W // p)
-            Sv = Fr * hw
+            Sv = (Fr // pt) * hw
             S = St + Sv
             ts = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32)
             if ts.numel() == 1 and B > 1:
@@ -358,6 +359,8 @@ class LoRATrainableTransformer:
             emb = dense.linear_smallm(e1, t.t2_w, t.t2_b, act_in=dense.ACT_SILU)
             x0 = torch.empty((B, S, D), dtype=BF16, device=dev)
             patches = dense.patchify(hs.view(B * Fr, Cc, H, W))
+            if pt > 1:                                             # [B, Fr/pt, pt, hw, Cpp] -> [.., hw, pt*Cpp] (the weight columns were permuted at load)
+                patches = patches.view(B, Fr // pt, pt, hw, -1).permute(0, 1, 3, 2, 4).reshape(B * Sv, -1).contiguous()
             epi = dense.EPI_BIAS
             if t.pos_embedding is not None:                        # CogVideoX-5B-I2V: learned positional embedding (frozen)
                 if t.pos_embedding.shape[1] < S:
@@ -387,7 +390,8 @@ class LoRATrainableTransformer:
         tok = _LoRALinear.apply(y, t.po_w, t.po_b, self._wt["po_t"], self.scaling, ())             # [B*S, p*p*C]
         tok = tok.view(B, S, -1)[:, St:]                                                             # video rows
         Co = c.out_channels
-        out = tok.reshape(B, Fr, H // p, W // p, Co, p, p).permute(0, 1, 4, 2, 5, 3, 6).reshape(B, Fr, Co, H, W)
+        # proj_out features are (pt, c, ph, pw) (rows permuted at load for pt > 1): token (f, hg, wg) -> frames f*pt .. f*pt + pt - 1
+        out = tok.reshape(B, Fr // pt, H // p, W // p, pt, Co, p, p).permute(0, 1, 4, 5, 2, 6, 3, 7).reshape(B, Fr, Co, H, W)
         return out
 
     __call__ = forward

@@ -38,6 +38,15 @@ class DPOSharedStep:
         x_lose = batch["x_lose"].to(dev).permute(0, 2, 1, 3, 4).float()
         prompt_emb = batch["prompt_emb"].to(dev)
         B = x_win.shape[0]
+        if (self.transformer.config.patch_size_t or 1) > 1:
+            # train/CogVideoX1.5-5B/03_train.py:134-144: the temporal-patch model needs even F, H, W; odd sizes are trimmed
+            _, Fr, _, H, W = x_win.shape
+            nF, nH, nW = Fr - Fr % 2, H - H % 2, W - W % 2
+            if (nF, nH, nW) != (Fr, H, W):
+                x_win = x_win[:, :nF, :, :nH, :nW].contiguous()
+                x_lose = x_lose[:, :nF, :, :nH, :nW].contiguous()
+                if noise is not None and tuple(noise.shape) != tuple(x_win.shape):
+                    noise = noise[:, :nF, :, :nH, :nW].contiguous()
         if timesteps is None:
             timesteps = torch.randint(0, self.scheduler.num_train_timesteps, (B,), device=dev, generator=generator)
         if noise is None:
