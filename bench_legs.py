@@ -235,90 +235,21 @@ def multi_gpu_legs(args, rank: int, world: int, dev, model, pipe, single_gpu_ste
         dist.barrier()
         torch.cuda.synchronize()
 
-    def make_group():
-        try:
-            return CfgPairPeerGroup(rank, world), "peer memory (exchange fused into the guidance + scheduler kernel over NVLink)"
-        except Exception as ex:                          # noqa: BLE001
-            return CfgPairGroup(rank, world), f"NCCL all-gather (peer-memory path unavailable: {type(ex).__name__})"
+    # One 2-rank NCCL group per CFG pair, created once and shared by every leg. The peer-memory group (exchange fused into the
+    # guidance + scheduler kernel) serves the CogVideoX leg; the Wan leg exchanges through NCCL on the same group: on 2 B200s the
+    # Wan leg never returned when it built a second peer group after the first (cause not isolated; profiles/r02_multi_gpu.md).
+    pair_nccl = CfgPairGroup(rank, world)
 
-    # ---- (i-a) CFG-pair shard, CogVideoX-5B: ranks (2p, 2p+1) run uncond / cond of prompt p
-    try:
-        grp, how = make_group()
-        ts = pipe.scheduler.set_timesteps(50)
-        gl = torch.Generator(device=dev).manual_seed(100 + grp.pair)          # identical latents and prompts inside a pair
-        lat = pipe.prepare_latents(1, 49, 480, 720, generator=gl)
-        pe = torch.randn(2, 226, 4096, generator=gl, device=dev).to(BF)
-        rope = pipe.rotary(13, 60, 90)
-        with torch.no_grad():
-            x = lat
-            for i in range(2):
-                x = pipe.denoise_step(x, pe, int(ts[i]), 6.0, rope, cfg_group=grp)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            n = 3
-            for i in range(n):
-                x = pipe.denoise_step(x, pe, int(ts[2 + i]), 6.0, rope, cfg_group=grp)
-            e1.record()
-            barrier()
-            step_ms = e0.elapsed_time(e1) / n
-            # one branch alone (no exchange, no update): what the step costs without the split's communication
-            xin = lat
-            tt = torch.full((1,), 999.0, device=dev)
-            fwd = lambda: model(hidden_states=xin, encoder_hidden_states=pe[:1], timestep=tt, image_rotary_emb=rope, return_dict=False)
-            fwd_ms = cuda_ms(fwd, 3, warmup=1)
-        both = [torch.empty_like(x) for _ in range(world)]
-        dist.all_gather(both, x.contiguous())
-        same = bool(torch.equal(both[2 * grp.pair], both[2 * grp.pair + 1]))
-        step_ms, fwd_ms = _max_over_ranks([step_ms, fwd_ms], dev)
-        out["cfg_pair_cogvideox"] = {
-            "workload": f"CogVideoX-5B T2V 49f 720x480, {world // 2} prompt(s), cond / uncond on the two GPUs of a pair", "exchange": how,
-            "ms_per_step": step_ms, "tokens_per_s": (world // 2) * 17550 / (step_ms / 1000.0),
-            "single_gpu_batched_ms_per_step": single_gpu_step_ms, "speedup_vs_single_gpu_batched": single_gpu_step_ms / step_ms,
-            "one_branch_forward_ms": fwd_ms, "exposed_exchange_and_update_ms": step_ms - fwd_ms,
-            "exchange_bytes_per_step_per_rank": 13 * 16 * 60 * 90 * 2, "latents_identical_inside_pair": same}
-        del grp
-    except Exception as ex:                              # noqa: BLE001
-        out["cfg_pair_cogvideox"] = {"error": f"{type(ex).__name__}: {ex}"}
+    def make_group(peer: bool):
+        if peer:
+            try:
+                return CfgPairPeerGroup(rank, world, share=pair_nccl), "peer memory (exchange fused into the guidance + scheduler kernel over NVLink)"
+            except Exception as ex:                      # noqa: BLE001
+                return pair_nccl, f"NCCL all-gather (peer-memory path unavailable: {type(ex).__name__})"
+        return pair_nccl, "NCCL all-gather inside the pair, then the fused guidance + scheduler kernel"
 
-    # ---- (i-b) CFG-pair shard, Wan2.2-TI2V-5B (BASELINE.json configs[3]: 4 GPUs = 2 prompts)
-    try:
-        from videogpa_b200.wan import WanConfig, WanDenoiseStep, WanTransformer3D, flow_sigmas
-        grp, how = make_group()
-        wm = WanTransformer3D.random_init(WanConfig.ti2v_5b(), seed=21, device=dev)
-        wstep = WanDenoiseStep(wm, guide_scale=5.0)
-        gw = torch.Generator(device=dev).manual_seed(200 + grp.pair)
-        wlat = torch.randn(48, 21, 44, 80, device=dev, generator=gw).to(BF)
-        wctx = torch.randn(512, 4096, device=dev, generator=gw).to(BF)
-        wnull = torch.zeros(1, 4096, device=dev, dtype=BF)
-        wS, whw = 21 * 22 * 40, 22 * 40
-        sig = flow_sigmas(50, 5.0)
-        wt = torch.full((1, wS), sig[0] * 1000.0); wt[:, :whw] = 0
-        xw = wstep(wlat, wt, sig[0], sig[1], wctx, wnull, cfg_group=grp, first_frame=wlat[:, :1])
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        n = 2
-        for i in range(n):
-            xw = wstep(xw, wt, sig[i + 1], sig[i + 2], wctx, wnull, cfg_group=grp, first_frame=wlat[:, :1])
-        e1.record()
-        barrier()
-        pair_ms = e0.elapsed_time(e1) / n
-        single_ms = cuda_ms(lambda: wstep(wlat, wt, sig[1], sig[2], wctx, wnull, first_frame=wlat[:, :1]), 1, warmup=1)
-        fwd_ms = cuda_ms(lambda: wm([wlat], wt, [wctx]), 2, warmup=1)
-        pair_ms, single_ms, fwd_ms = _max_over_ranks([pair_ms, single_ms, fwd_ms], dev)
-        out["cfg_pair_wan"] = {
-            "workload": f"Wan2.2-TI2V-5B 81f 1280x704 (S = 18 480), {world // 2} prompt(s), cond / uncond on the two GPUs of a pair"
-                        + ("" if world == 4 else f" (BASELINE.json configs[3] names 4 GPUs; this run has {world})"),
-            "exchange": how, "ms_per_step": pair_ms, "tokens_per_s": (world // 2) * wS / (pair_ms / 1000.0),
-            "single_gpu_two_forwards_ms_per_step": single_ms, "speedup_vs_single_gpu": single_ms / pair_ms,
-            "one_branch_forward_ms": fwd_ms, "exposed_exchange_and_update_ms": pair_ms - fwd_ms,
-            "exchange_bytes_per_step_per_rank": 48 * 21 * 44 * 80 * 2, "finite": bool(torch.isfinite(xw.float()).all().item())}
-        del wm, wstep, xw, grp
-        torch.cuda.empty_cache()
-    except Exception as ex:                              # noqa: BLE001
-        out["cfg_pair_wan"] = {"error": f"{type(ex).__name__}: {ex}"}
-
+    # Order: the legs that only use NCCL collectives first (clip + gather, DDP step, Wan pair), the peer-memory leg last, so that a
+    # problem in the symmetric-memory path cannot take the others with it (bench.py bounds the whole sequence with a watchdog).
     # ---- (ii) BASELINE.json configs[2]: CogVideoX-5B-I2V, one prompt per GPU, 50 steps + VAE decode + gather of the uint8 frames
     try:
         from videogpa_b200.pipeline import CogVideoXDenoisePipeline
@@ -341,6 +272,7 @@ def multi_gpu_legs(args, rank: int, world: int, dev, model, pipe, single_gpu_ste
         with torch.no_grad():
             ipipe(prompt, negative, num_inference_steps=2, guidance_scale=6.0, generator=gi, image_latents=img_lat)    # warm-up
             dec.decode(torch.zeros(1, 16, 13, 60, 90, device=dev, dtype=BF))
+            gather_frames(torch.zeros(1, 480, 720, 3, dtype=torch.uint8, device=dev), rank, world)    # NCCL send/recv channels are set up once per process (200 ms)
             barrier()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
@@ -417,4 +349,82 @@ def multi_gpu_legs(args, rank: int, world: int, dev, model, pipe, single_gpu_ste
         torch.cuda.empty_cache()
     except Exception as ex:                              # noqa: BLE001
         out["dpo_ddp_step"] = {"error": f"{type(ex).__name__}: {ex}"}
+    # ---- (i-b) CFG-pair shard, Wan2.2-TI2V-5B (BASELINE.json configs[3]: 4 GPUs = 2 prompts)
+    try:
+        from videogpa_b200.wan import WanConfig, WanDenoiseStep, WanTransformer3D, flow_sigmas
+        grp, how = make_group(peer=False)
+        wm = WanTransformer3D.random_init(WanConfig.ti2v_5b(), seed=21, device=dev)
+        wstep = WanDenoiseStep(wm, guide_scale=5.0)
+        gw = torch.Generator(device=dev).manual_seed(200 + grp.pair)
+        wlat = torch.randn(48, 21, 44, 80, device=dev, generator=gw).to(BF)
+        wctx = torch.randn(512, 4096, device=dev, generator=gw).to(BF)
+        wnull = torch.zeros(1, 4096, device=dev, dtype=BF)
+        wS, whw = 21 * 22 * 40, 22 * 40
+        sig = flow_sigmas(50, 5.0)
+        wt = torch.full((1, wS), sig[0] * 1000.0); wt[:, :whw] = 0
+        xw = wstep(wlat, wt, sig[0], sig[1], wctx, wnull, cfg_group=grp, first_frame=wlat[:, :1])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 2
+        for i in range(n):
+            xw = wstep(xw, wt, sig[i + 1], sig[i + 2], wctx, wnull, cfg_group=grp, first_frame=wlat[:, :1])
+        e1.record()
+        barrier()
+        pair_ms = e0.elapsed_time(e1) / n
+        single_ms = cuda_ms(lambda: wstep(wlat, wt, sig[1], sig[2], wctx, wnull, first_frame=wlat[:, :1]), 1, warmup=1)
+        fwd_ms = cuda_ms(lambda: wm([wlat], wt, [wctx]), 2, warmup=1)
+        pair_ms, single_ms, fwd_ms = _max_over_ranks([pair_ms, single_ms, fwd_ms], dev)
+        out["cfg_pair_wan"] = {
+            "workload": f"Wan2.2-TI2V-5B 81f 1280x704 (S = 18 480), {world // 2} prompt(s), cond / uncond on the two GPUs of a pair"
+                        + ("" if world == 4 else f" (BASELINE.json configs[3] names 4 GPUs; this run has {world})"),
+            "exchange": how, "ms_per_step": pair_ms, "tokens_per_s": (world // 2) * wS / (pair_ms / 1000.0),
+            "single_gpu_two_forwards_ms_per_step": single_ms, "speedup_vs_single_gpu": single_ms / pair_ms,
+            "one_branch_forward_ms": fwd_ms, "exposed_exchange_and_update_ms": pair_ms - fwd_ms,
+            "exchange_bytes_per_step_per_rank": 48 * 21 * 44 * 80 * 2, "finite": bool(torch.isfinite(xw.float()).all().item())}
+        del wm, wstep, xw, grp
+        torch.cuda.empty_cache()
+    except Exception as ex:                              # noqa: BLE001
+        out["cfg_pair_wan"] = {"error": f"{type(ex).__name__}: {ex}"}
+
+    # ---- (i-a) CFG-pair shard, CogVideoX-5B: ranks (2p, 2p+1) run uncond / cond of prompt p
+    try:
+        grp, how = make_group(peer=True)
+        ts = pipe.scheduler.set_timesteps(50)
+        gl = torch.Generator(device=dev).manual_seed(100 + grp.pair)          # identical latents and prompts inside a pair
+        lat = pipe.prepare_latents(1, 49, 480, 720, generator=gl)
+        pe = torch.randn(2, 226, 4096, generator=gl, device=dev).to(BF)
+        rope = pipe.rotary(13, 60, 90)
+        with torch.no_grad():
+            x = lat
+            for i in range(2):
+                x = pipe.denoise_step(x, pe, int(ts[i]), 6.0, rope, cfg_group=grp)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n = 3
+            for i in range(n):
+                x = pipe.denoise_step(x, pe, int(ts[2 + i]), 6.0, rope, cfg_group=grp)
+            e1.record()
+            barrier()
+            step_ms = e0.elapsed_time(e1) / n
+            # one branch alone (no exchange, no update): what the step costs without the split's communication
+            xin = lat
+            tt = torch.full((1,), 999.0, device=dev)
+            fwd = lambda: model(hidden_states=xin, encoder_hidden_states=pe[:1], timestep=tt, image_rotary_emb=rope, return_dict=False)
+            fwd_ms = cuda_ms(fwd, 3, warmup=1)
+        both = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(both, x.contiguous())
+        same = bool(torch.equal(both[2 * grp.pair], both[2 * grp.pair + 1]))
+        step_ms, fwd_ms = _max_over_ranks([step_ms, fwd_ms], dev)
+        out["cfg_pair_cogvideox"] = {
+            "workload": f"CogVideoX-5B T2V 49f 720x480, {world // 2} prompt(s), cond / uncond on the two GPUs of a pair", "exchange": how,
+            "ms_per_step": step_ms, "tokens_per_s": (world // 2) * 17550 / (step_ms / 1000.0),
+            "single_gpu_batched_ms_per_step": single_gpu_step_ms, "speedup_vs_single_gpu_batched": single_gpu_step_ms / step_ms,
+            "one_branch_forward_ms": fwd_ms, "exposed_exchange_and_update_ms": step_ms - fwd_ms,
+            "exchange_bytes_per_step_per_rank": 13 * 16 * 60 * 90 * 2, "latents_identical_inside_pair": same}
+        del grp
+    except Exception as ex:                              # noqa: BLE001
+        out["cfg_pair_cogvideox"] = {"error": f"{type(ex).__name__}: {ex}"}
+
     return out

@@ -93,15 +93,19 @@ __device__ __forceinline__ float softplus_f(float x) {  // log(1 + exp(x)), stab
 __global__ void dpo_finalize_kernel(const double* __restrict__ partial, int B, long long n, int blocks_per_sample,
                                     float beta, float label_smoothing, int loss_type, float* __restrict__ out5,
                                     float* __restrict__ err4, float* __restrict__ coef) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp: lane l sums the block partials l, l + 32, ... in order, then a fixed shuffle tree (deterministic; a single
+  // thread walking several hundred dependent loads cost 17 us, more than the pass over the six tensors)
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   float loss = 0.f, margin = 0.f, wr = 0.f, lr = 0.f, acc = 0.f;
   for (int b = 0; b < B; ++b) {
     double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = 0; k < blocks_per_sample; ++k)
+    for (int k = lane; k < blocks_per_sample; k += 32)
       for (int c = 0; c < 4; ++c) s[c] += partial[(static_cast<long long>(b) * blocks_per_sample + k) * 4 + c];
+    for (int c = 0; c < 4; ++c) s[c] = warp_sum_d(s[c]);
     const float mw = static_cast<float>(s[0] / static_cast<double>(n)), ml = static_cast<float>(s[1] / static_cast<double>(n));
     const float rw = static_cast<float>(s[2] / static_cast<double>(n)), rl = static_cast<float>(s[3] / static_cast<double>(n));
-    if (err4) { err4[0 * B + b] = mw; err4[1 * B + b] = ml; err4[2 * B + b] = rw; err4[3 * B + b] = rl; }
+    if (err4 && lane == 0) { err4[0 * B + b] = mw; err4[1 * B + b] = ml; err4[2 * B + b] = rw; err4[3 * B + b] = rl; }
     const float win_diff = rw - mw, lose_diff = rl - ml;                 // loss.py:82-83
     const float logit = beta * (win_diff - lose_diff);                   // loss.py:93
     float l, dl;
@@ -125,13 +129,14 @@ __global__ void dpo_finalize_kernel(const double* __restrict__ partial, int B, l
     const float w_rew = -mw, l_rew = -ml;                                // loss.py:86-88
     margin += w_rew - l_rew; wr += w_rew; lr += l_rew;
     acc += (w_rew > l_rew) ? 1.0f : 0.f;
-    if (coef) {
+    if (coef && lane == 0) {
       // dlogit/d(model_win_err) = -beta, dlogit/d(model_lose_err) = +beta; mean over B
       coef[0 * B + b] = (loss_type == VGPA_DPO_SFT) ? 1.0f / static_cast<float>(B) : dl * (-beta) / static_cast<float>(B);
       coef[1 * B + b] = (loss_type == VGPA_DPO_SFT) ? 0.f : dl * (beta) / static_cast<float>(B);
     }
   }
   const float inv = 1.0f / static_cast<float>(B);
+  if (lane != 0) return;
   out5[0] = loss * inv; out5[1] = margin * inv; out5[2] = wr * inv; out5[3] = lr * inv; out5[4] = acc * inv;
 }
 
@@ -157,7 +162,7 @@ dpo_backward_kernel(const void* v_win, int bf_vw, const void* v_lose, int bf_vl,
 }
 
 int dl_blocks_per_sample(int B, long long n) {
-  long long need = (n + DL_THREADS * 4 * 8 - 1) / (DL_THREADS * 4 * 8);   // >= 8 vector iterations per thread
+  long long need = (n + DL_THREADS * 4 * 2 - 1) / (DL_THREADS * 4 * 2);   // >= 2 vector iterations per thread: one pair (1.1 M elements) fills 148 SMs
   long long want = (148LL * 8 + B - 1) / B;
   if (need > want) need = want;
   if (need < 1) need = 1;

@@ -328,6 +328,9 @@ mvcs_pairs_kernel(const float* __restrict__ depths, const float* __restrict__ pa
   __syncthreads();
   const float* di = depths + (static_cast<long long>(clip) * T + pair_i) * H * W;
   const float* dj = di + static_cast<long long>(H) * W;
+  // keep the gather base in a register pair: under the 64-register cap the compiler otherwise re-derives it from the kernel
+  // parameters inside the loop (a dozen 64-bit integer instructions per pixel pair)
+  asm volatile("" : "+l"(dj));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // constants of the inner loop (scalar registers: the packed instructions broadcast a 32-bit operand to both halves)
   const float m0 = s_fp[0], m3 = s_fp[3], m6 = s_fp[6], z0 = s_fp[12];

@@ -60,13 +60,17 @@ def shard_contiguous(items, rank: int, world: int):
 class CfgPairGroup:
     """Ranks (2p, 2p+1) hold the uncond / cond branch of prompt-group p."""
 
-    def __init__(self, rank: int, world: int):
+    def __init__(self, rank: int, world: int, share: "CfgPairGroup | None" = None):
+        """share: reuse the 2-rank process group of an existing CfgPairGroup instead of creating new ones."""
         if world % 2 != 0:
             raise RuntimeError("CFG-pair sharding needs an even number of ranks")
         self.rank, self.world = rank, world
         self.pair = rank // 2
         self.branch = rank % 2            # 0 = uncond (negative prompt), 1 = cond
         self.group = None
+        if share is not None:
+            self.group = share.group
+            return
         for p in range(world // 2):       # every rank must take part in every new_group call
             g = dist.new_group(ranks=[2 * p, 2 * p + 1])
             if p == self.pair:
@@ -90,8 +94,8 @@ class CfgPairPeerGroup(CfgPairGroup):
     collective library call is on the data path. Falls back to nothing: construction raises if peer access is unavailable.
     """
 
-    def __init__(self, rank: int, world: int):
-        super().__init__(rank, world)
+    def __init__(self, rank: int, world: int, share: "CfgPairGroup | None" = None):
+        super().__init__(rank, world, share)
         self._buf = None
         self._hdl = None
         self._n = 0
