@@ -421,8 +421,14 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
              "vgpa_linear_bf16: pointers must be 16-byte aligned");
   int BN = (a->N % 256 == 0) ? 256 : 64;
   // skinny problems (T5 prompt encoder: M = 226) are bound by streaming W once from HBM: with 128x256 tiles fewer CTAs
-  // than SMs would be pulling it, so use 128x64 tiles there
-  if (BN == 256 && static_cast<long long>((a->M + BM - 1) / BM) * (a->N / 256) < 148) BN = 64;
+  // than SMs would be pulling it, so use narrower tiles there. Every tile also re-fetches its 128-row activation tile from
+  // L2, which is 2/3 of an SM's ingest at BN = 64 and 1/2 at BN = 128: take 128 whenever that still gives ~one tile per SM
+  // (T5: the fused q|k|v and the wi projections), 64 otherwise (N = 4096: o and wo).
+  if (BN == 256 && static_cast<long long>((a->M + BM - 1) / BM) * (a->N / 256) < 148) {
+    static int k_bn128 = -1;
+    if (k_bn128 < 0) { const char* e = getenv("VGPA_GEMM_BN128"); k_bn128 = e ? atoi(e) : 1; }
+    BN = (k_bn128 && a->N % 128 == 0 && static_cast<long long>((a->M + BM - 1) / BM) * (a->N / 128) >= 120) ? 128 : 64;
+  }
   // cluster of 2 with W-tile multicast for the big GEMMs (development knob VGPA_GEMM_CLUSTER=0 turns it off)
   static int use_cluster = -1;
   if (use_cluster < 0) {
@@ -493,7 +499,8 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
   case EPI:                                                                              \
     return BN == 256 ? (CL == 2 ? launch_gemm<256, EPI, 2>(tmA, tmB, a->M, a->N, a->K, ep, s)    \
                                 : launch_gemm<256, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s))   \
-                     : launch_gemm<64, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s);
+           : BN == 128 ? launch_gemm<128, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s)             \
+                       : launch_gemm<64, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s);
   switch (a->epilogue) {
     VGPA_GEMM_DISPATCH(VGPA_EPI_BIAS)
     VGPA_GEMM_DISPATCH(VGPA_EPI_BIAS_GELU)
