@@ -93,10 +93,9 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_block_sample(threads: int, repeats: int = 1):
-    """Time the CPU oracle (torch restatement of the diffusers math) on ONE transformer block at the full
-    sequence, B = 1, bf16, and extrapolate to a denoise step (42 blocks x 2 CFG branches). Returns
-    (tokens_per_s, seconds_per_block, description)."""
+def cpu_block_setup(threads: int):
+    """Inputs of the CPU arm's bounded sample: ONE CogVideoXBlock of the oracle (torch restatement of the diffusers math) at the
+    full sequence, B = 1, bf16. A denoise step is 42 blocks x 2 CFG branches = 84 such samples."""
     import torch
     from oracle import dit_torch as O
     torch.set_num_threads(threads)
@@ -108,41 +107,60 @@ def cpu_block_sample(threads: int, repeats: int = 1):
     enc = torch.randn(1, S_TEXT, D, generator=g).to(torch.bfloat16)
     emb = torch.randn(1, cfg.time_embed_dim, generator=g).to(torch.bfloat16)
     rope = O.rope_3d(cfg, LAT_F, LAT_H, LAT_W)
-    best = float("inf")
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
+
+    def run():
+        with torch.no_grad():
             O.block_forward(sd, cfg, 0, hs, enc, emb, rope)
-            best = min(best, time.perf_counter() - t0)
-    step_s = best * 42 * 2
-    return S_VIDEO / step_s, best, "1 of 42 CogVideoXBlocks at S=17776, B=1, bf16, torch CPU; x42 blocks x2 CFG branches extrapolated"
+    return run
+
+
+CPU_SAMPLE = "1 of 42 CogVideoXBlocks at S=17776, B=1, bf16, torch CPU = 1/84 of a denoise step (42 blocks x 2 CFG branches)"
+
+
+def cpu_block_sample(threads: int, repeats: int = 1):
+    """-> (tokens_per_s, seconds_per_block, description): the best of `repeats` timed samples, extrapolated to a step."""
+    run = cpu_block_setup(threads)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        run()
+        best = min(best, time.perf_counter() - t0)
+    return S_VIDEO / (best * 84), best, CPU_SAMPLE + "; x84 extrapolated"
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores. diffusers cannot be installed here
+    (DESIGN.md), so the denoise half is the oracle port; a *step* of this arm is the bounded sample (one block = 1/84 of a
+    denoise step = 17 550 / 84 latent tokens), timed K times after W warm-up samples: `ms_per_step` is the measured time of a
+    sample and `value` = tokens-equivalent per second, so steps x ms_per_step is what was really timed. The scorer half runs
+    the reference's own files (oracle/_ref)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vals = []
-    for _ in range(max(0, args.warmup if args.warmup < 2 else 1)):
-        cpu_block_sample(threads)
+    run = cpu_block_setup(threads)
+    for _ in range(min(max(args.warmup, 0), 2)):
+        run()
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
-        v, sec_block, desc = cpu_block_sample(threads)
-        vals.append(v)
-    value = sum(vals) / len(vals)
+        run()
+    sec_sample = (time.perf_counter() - t_all0) / max(1, args.steps)
+    tokens_per_sample = S_VIDEO / 84.0
+    value = tokens_per_sample / sec_sample
     try:
         import bench_legs
         scorer = bench_legs.cpu_scorer_baselines()
     except Exception as ex:      # noqa: BLE001
         scorer = {"error": f"{type(ex).__name__}: {ex}"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * S_VIDEO / value, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1000.0 * sec_sample, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "layers": 42, "tokens_per_step_per_gpu": S_VIDEO, "sequence": S_TEXT + S_VIDEO,
+                       "step_of_this_arm": CPU_SAMPLE, "tokens_per_timed_step": tokens_per_sample,
                        "note": "CPU arm: oracle/dit_torch.py restatement of the reference's diffusers path on the host cores "
-                               "(diffusers/peft are not installable offline, DESIGN.md); each step = a bounded sample, see cpu_baseline.sample"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
-                             "sample_fraction_of_a_step": 1.0 / 84.0},
+                               "(diffusers/peft are not installable offline, DESIGN.md); a full step would be 84 samples "
+                               f"= {84.0 * sec_sample:.0f} s"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE,
+                             "sample_fraction_of_a_step": 1.0 / 84.0, "seconds_per_sample": sec_sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             # the scorer half of the path CAN run the reference's own files on this box (oracle/_ref, byte-compiled from
             # /root/reference): MVCS (BASELINE.json's second metric), project_points, DPOLoss
@@ -300,6 +318,14 @@ def run_ours(args, rank, world, local):
             multi["error"] = f"{type(ex).__name__}: {ex}"
         done.set()
     if rank != 0:
+        return
+    if args.primary_only:                                  # dev: the primary measurement alone (no secondary legs, no baselines)
+        L = cfg.num_layers
+        attn_avg = sum(attn_ms) / max(1, len(attn_ms))
+        print(json.dumps({"metric": METRIC, "value": world * S_VIDEO * args.steps / (ms_max / 1000.0), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "layers": L,
+                          "attention_avg_launch_ms": attn_avg, "attention_share": sum(attn_ms) / ms_max if ms_max > 0 else None,
+                          "clocks": clocks, "finite": finite, "primary_only": True}), flush=True)
         return
     emit(multi)
 
@@ -518,10 +544,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=0, help="debug: run fewer transformer blocks (the number is printed in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--primary-only", action="store_true", help="dev: print only the primary measurement (not a valid bench line)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager GPU baseline of the step (N = 1)")
     ap.add_argument("--no-multi-gpu-legs", action="store_true", help="N >= 2: skip the CFG-pair / clip / DDP legs")
     ap.add_argument("--e2e-steps", type=int, default=50, help="N >= 2: denoise steps of the prompt-sharded clip leg")
-    ap.add_argument("--multi-gpu-timeout", type=float, default=420.0, help="N >= 2: bound (s) on the multi-GPU legs before the line is printed without them")
+    ap.add_argument("--multi-gpu-timeout", type=float, default=240.0, help="N >= 2: bound (s) on the multi-GPU legs before the line is printed without them")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

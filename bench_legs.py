@@ -241,12 +241,14 @@ def multi_gpu_legs(args, rank: int, world: int, dev, model, pipe, single_gpu_ste
     pair_nccl = CfgPairGroup(rank, world)
 
     def make_group(peer: bool):
-        if peer:
+        if peer and world == 2:                          # with several pairs (4 GPUs) the peer-memory leg never returned: one pair only
+
             try:
                 return CfgPairPeerGroup(rank, world, share=pair_nccl), "peer memory (exchange fused into the guidance + scheduler kernel over NVLink)"
             except Exception as ex:                      # noqa: BLE001
                 return pair_nccl, f"NCCL all-gather (peer-memory path unavailable: {type(ex).__name__})"
-        return pair_nccl, "NCCL all-gather inside the pair, then the fused guidance + scheduler kernel"
+        return pair_nccl, ("NCCL all-gather inside the pair, then the fused guidance + scheduler kernel"
+                           + (" (the peer-memory exchange is only used with one pair: it hung with two pairs on 4 GPUs)" if peer else ""))
 
     # Order: the legs that only use NCCL collectives first (clip + gather, DDP step, Wan pair), the peer-memory leg last, so that a
     # problem in the symmetric-memory path cannot take the others with it (bench.py bounds the whole sequence with a watchdog).
@@ -272,7 +274,7 @@ def multi_gpu_legs(args, rank: int, world: int, dev, model, pipe, single_gpu_ste
         with torch.no_grad():
             ipipe(prompt, negative, num_inference_steps=2, guidance_scale=6.0, generator=gi, image_latents=img_lat)    # warm-up
             dec.decode(torch.zeros(1, 16, 13, 60, 90, device=dev, dtype=BF))
-            gather_frames(torch.zeros(1, 480, 720, 3, dtype=torch.uint8, device=dev), rank, world)    # NCCL send/recv channels are set up once per process (200 ms)
+            gather_frames(torch.zeros(49, 480, 720, 3, dtype=torch.uint8, device=dev), rank, world)   # first collective of this size: protocol / buffer set-up
             barrier()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()

@@ -91,10 +91,15 @@ class CfgPairPeerGroup(CfgPairGroup):
     (peer-mapped) buffer, and `vgpa_cfg_scheduler_step` reads the partner's half straight through the peer pointer while it
     combines guidance and applies the scheduler update: one kernel does the transfer and the math. Two device-side barriers
     on the symmetric-memory signal pads order "partner has written" before and "partner has read" after the kernel; no
-    collective library call is on the data path. Falls back to nothing: construction raises if peer access is unavailable.
+    collective library call is on the data path. Falls back to nothing: construction raises if peer access is unavailable,
+    and for more than one pair (world size > 2).
     """
 
     def __init__(self, rank: int, world: int, share: "CfgPairGroup | None" = None):
+        if world != 2:
+            # measured on 4 B200s (two pairs): the first fused step never returned (profiles/r02_multi_gpu.md); until the
+            # symmetric-memory rendezvous on 2-rank subgroups is understood, several pairs exchange through CfgPairGroup (NCCL)
+            raise RuntimeError("CfgPairPeerGroup is validated for one CFG pair (world size 2); use CfgPairGroup with more ranks")
         super().__init__(rank, world, share)
         self._buf = None
         self._hdl = None
@@ -126,20 +131,33 @@ class CfgPairPeerGroup(CfgPairGroup):
 
 def gather_frames(frames: torch.Tensor, rank: int, world: int, dst: int = 0):
     """Final decoded-frame gather: every rank contributes a [n_i, ...] uint8 tensor with identical trailing
-    shape; rank `dst` receives the list ordered by rank, the others get None."""
+    shape; rank `dst` receives the list ordered by rank, the others get None.
+
+    One all-gather collective into a [world, n_max, ...] buffer (NCCL: ring / NVLS over NVSwitch; 50.8 MB per 49-frame clip):
+    the send/recv pairs of a rooted gather set up point-to-point channels on first use and measured 0.2-0.9 s on 2-4 B200s,
+    the all-gather runs on the communicator's existing rings."""
     if world == 1:
         return [frames]
     n = torch.tensor([frames.shape[0]], dtype=torch.int64, device=frames.device)
     counts = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(counts, n)
-    nmax = int(max(int(c.item()) for c in counts))
-    pad = torch.zeros((nmax,) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
-    pad[:frames.shape[0]] = frames
-    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(counts)
+    if frames.shape[0] == nmax:
+        pad = frames.contiguous()
+    else:
+        pad = torch.zeros((nmax,) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
+        pad[:frames.shape[0]] = frames
+    if dist.get_backend() == "nccl":
+        buf = torch.empty((world,) + tuple(pad.shape), dtype=pad.dtype, device=pad.device)
+        dist.all_gather_into_tensor(buf, pad)
+        bufs = list(buf.unbind(0))
+    else:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad)
     if rank != dst:
         return None
-    return [b[:int(c.item())] for b, c in zip(bufs, counts)]
+    return [b[:c] for b, c in zip(bufs, counts)]
 
 
 def gather_scores(scores: torch.Tensor, rank: int, world: int):
