@@ -283,20 +283,24 @@ def multi_gpu_legs(args, rank: int, world: int, dev, model, pipe, single_gpu_ste
             frames = dec.decode(lat.permute(0, 2, 1, 3, 4) / 0.7).sample                                              # [1, 3, 49, 480, 720]
             u8 = ((frames[0].float().clamp(-1, 1) + 1.0) * 127.5).round().to(torch.uint8).permute(1, 2, 3, 0).contiguous()   # [49, 480, 720, 3]
             ev[2].record()
+            barrier()                                    # ranks finish 50 steps ~1 % apart: keep that skew out of the collective's time
+            evb = torch.cuda.Event(enable_timing=True)
+            evb.record()
             got = gather_frames(u8, rank, world)
             ev[3].record()
             barrier()
-        den_ms, dec_ms, gat_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+        den_ms, dec_ms, gat_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), evb.elapsed_time(ev[3])
+        skew_ms = ev[2].elapsed_time(evb)
         total_ms = ev[0].elapsed_time(ev[3])
         ok = rank != 0 or (len(got) == world and all(tuple(f.shape) == (49, 480, 720, 3) for f in got))
-        den_ms, dec_ms, gat_ms, total_ms = _max_over_ranks([den_ms, dec_ms, gat_ms, total_ms], dev)
+        den_ms, dec_ms, gat_ms, total_ms, skew_ms = _max_over_ranks([den_ms, dec_ms, gat_ms, total_ms, skew_ms], dev)
         nbytes = 49 * 480 * 720 * 3
         out["prompt_shard_clip"] = {
             "workload": f"CogVideoX-5B-I2V (in_channels 32, learned positional embedding; a merged LoRA does not change the FLOPs), 49f 720x480, "
                         f"one prompt per GPU x {world} GPUs, {steps} DDIM steps + tiled VAE decode + gather of the uint8 frames to rank 0",
-            "denoise_ms": den_ms, "vae_decode_and_uint8_ms": dec_ms, "frame_gather_ms": gat_ms, "total_ms": total_ms,
+            "denoise_ms": den_ms, "vae_decode_and_uint8_ms": dec_ms, "frame_gather_ms": gat_ms, "wait_for_slowest_rank_ms": skew_ms, "total_ms": total_ms,
             "clips_per_hour_all_gpus": world * 3600.0 * 1000.0 / total_ms, "gather_bytes_per_rank": nbytes,
-            "gather_gbs_into_rank0": (world - 1) * nbytes / (gat_ms / 1000.0) / 1e9 if gat_ms > 0 else None, "gather_ok": ok,
+            "gather_gbs_per_rank": (world - 1) * nbytes / (gat_ms / 1000.0) / 1e9 if gat_ms > 0 else None, "gather_ok": ok,
             "tokens_per_s_all_gpus": world * 17550 * steps / (den_ms / 1000.0)}
         del imodel, dec, ipipe, lat, frames, u8, got
         torch.cuda.empty_cache()

@@ -129,6 +129,16 @@ def test_sharding_rules():
     assert shard_contiguous([], 0, 2) == [] and shard_round_robin([1], 1, 2) == []
 
 
+def test_peer_pair_group_refuses_several_pairs():
+    """The fused peer-memory exchange is validated for one CFG pair only (it hung with two pairs on 4 GPUs,
+    profiles/r02_multi_gpu.md): more ranks must get an error, not a hang."""
+    from videogpa_b200.parallel import CfgPairPeerGroup
+    with pytest.raises(RuntimeError, match="one CFG pair"):
+        CfgPairPeerGroup(0, 4)
+    with pytest.raises(RuntimeError):
+        CfgPairPeerGroup(1, 8)
+
+
 def test_product_path_fails_loudly_without_cuda():
     """No CPU fallback: CPU tensors are rejected by the host wrappers."""
     from videogpa_b200 import dense

@@ -6,7 +6,7 @@ timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mas
    > gpurun_out/r02c5_bench_n2.json 2> gpurun_out/r02c5_bench_n2.err
 echo "bench n2 rc=$? wall=${SECONDS}s" >> gpurun_out/r02c5_gpus.log
 SECONDS=0
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --steps 2 --warmup 1 \
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --steps 3 --warmup 1 \
    > gpurun_out/r02c5_ref_n2.json 2> gpurun_out/r02c5_ref_n2.err
 echo "ref n2 rc=$? wall=${SECONDS}s" >> gpurun_out/r02c5_gpus.log
 cat gpurun_out/r02c5_gpus.log; tail -5 gpurun_out/r02c5_bench_n2.err; head -c 600 gpurun_out/r02c5_bench_n2.json; echo; python - <<'PY'
