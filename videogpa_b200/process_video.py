@@ -49,11 +49,13 @@ class VideoProcessor:
 
     # ------------------------------------------------------------------ reference entry point
     def process(self, video_path, thresholds, num_frames, save_visuals=False, out_dir=None):
-        if self.backbone_fn is None or self.frame_sampler is None:
-            raise RuntimeError("VideoProcessor.process needs injected `frame_sampler(video_path, n_frames)` and `backbone_fn(frames)`: "
-                               "video decoding and the VGGT / DA3 backbones are third-party and out of scope; "
-                               "use process_predictions(...) when predictions are already available")
-        frames = self.frame_sampler(video_path, n_frames=num_frames)
+        if self.backbone_fn is None:
+            raise RuntimeError("VideoProcessor.process needs an injected `backbone_fn(frames)`: the VGGT / DA3 backbones are "
+                               "third-party and out of scope; use process_predictions(...) when predictions are already available")
+        sampler = self.frame_sampler
+        if sampler is None:                              # pipelines/process_video.py:70 -> utils.video_utils.sample_uniform_frames
+            from .video_io import sample_uniform_frames as sampler
+        frames = sampler(video_path, n_frames=num_frames)
         preds = self.backbone_fn(frames)
         return self.process_predictions(preds, thresholds, frames_np=frames, save_visuals=save_visuals, out_dir=out_dir)
 
