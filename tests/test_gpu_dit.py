@@ -52,21 +52,61 @@ def test_attention(lib, B, H, S, Skv):
     assert relerr(out, ref) < 1e-2                                   # P is rounded to bf16 before PV, output to bf16
 
 
-def test_attention_four_warpgroup_variant_matches(lib):
-    """The alternative head_dim-64 kernel (attention_d64x4_sm100.cu, VGPA_ATTN_X4=1) is selected per process through an
-    environment knob: run it in a subprocess and compare with torch SDPA on the same seeded inputs."""
-    import os, subprocess, sys
-    code = ("import torch, torch.nn.functional as F, sys; sys.path.insert(0, '.'); from videogpa_b200 import dense; torch.manual_seed(0);"
-            "q=torch.randn(2,700,128,device='cuda').bfloat16(); kv=torch.randn(2,517,256,device='cuda').bfloat16();"
-            "o=dense.attention(q,kv[...,:128],kv[...,128:],2);"
-            "sp=lambda t,n: t.reshape(2,n,2,64).transpose(1,2).float();"
-            "r=F.scaled_dot_product_attention(sp(q,700),sp(kv[...,:128],517),sp(kv[...,128:],517)).transpose(1,2).reshape(2,700,128);"
-            "print('ERR', ((o.float()-r).abs().max()/r.abs().max()).item())")
-    env = dict(os.environ, VGPA_ATTN_X4="1", VGPA_ATTN_NPOLY="0")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    assert float(out.stdout.split("ERR")[1]) < 1e-2
+def test_attention_exact_kernel_and_mixed_heads(lib):
+    """vgpa_attention_bf16 serves a (batch, head) with the bounded-softmax kernel when max|q| max|k| scale log2(e) <= 90 and with
+    the exact online-softmax kernel otherwise. (i) exact=True forces the online-softmax kernel for every head; (ii) a call whose
+    heads fall on both sides of the bound; (iii) all heads above it. All against torch SDPA in fp32."""
+    from videogpa_b200 import dense
+    torch.manual_seed(3)
+    B, H, S, Skv = 2, 3, 700, 517
+    D = H * 64
+    sp = lambda t, n: t.reshape(B, n, H, 64).transpose(1, 2).float()
+    ref_of = lambda q, k, v: F.scaled_dot_product_attention(sp(q, S), sp(k, Skv), sp(v, Skv)).transpose(1, 2).reshape(B, S, D)
+    q = torch.randn(B, S, D, device="cuda").to(BF)
+    k = torch.randn(B, Skv, D, device="cuda").to(BF)
+    v = torch.randn(B, Skv, D, device="cuda").to(BF)
+    ref = ref_of(q, k, v)
+    fast = dense.attention(q, k, v, H)
+    exact = dense.attention(q, k, v, H, exact=True)
+    assert relerr(fast, ref) < 1e-2 and relerr(exact, ref) < 1e-2
+    # head 1 gets large q and k: |q||k| / 8 * log2(e) ~ 6 * 8 * 6 * 8 / 8 * 1.44 = 415 > 90 -> exact kernel; heads 0 and 2 stay bounded
+    q2, k2 = q.clone(), k.clone()
+    q2[..., 64:128] *= 6.0
+    k2[..., 64:128] *= 6.0
+    out = dense.attention(q2, k2, v, H)
+    assert torch.isfinite(out.float()).all() and relerr(out, ref_of(q2, k2, v)) < 1e-2
+    q3, k3 = q * 6.0, k * 6.0                                        # every head above the bound
+    out3 = dense.attention(q3.to(BF), k3.to(BF), v, H)
+    assert relerr(out3, ref_of(q3.to(BF), k3.to(BF), v)) < 1e-2
+
+
+def test_qkv_epilogue_vs_torch(lib):
+    """The fused QKV epilogue (bias, per-head LayerNorm(64, eps 1e-6, affine) on q and k, interleaved-pair RoPE on the video rows)
+    against plain torch ops — F.linear, F.layer_norm and the rotation written out — without going through oracle/dit_torch.py."""
+    from videogpa_b200 import dense
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, S, St, D, H = 2, 300, 18, 256, 4
+    x = torch.randn(B * S, D, device="cuda", generator=g).to(BF)
+    w = (torch.randn(3 * D, D, device="cuda", generator=g) * 0.05).to(BF)
+    bias = (torch.randn(3 * D, device="cuda", generator=g) * 0.1).to(BF)
+    lnq = (1.0 + 0.1 * torch.randn(64, device="cuda", generator=g), 0.1 * torch.randn(64, device="cuda", generator=g))
+    lnk = (1.0 + 0.1 * torch.randn(64, device="cuda", generator=g), 0.1 * torch.randn(64, device="cuda", generator=g))
+    ang = torch.rand(S - St, 32, device="cuda", generator=g) * 6.28
+    cos, sin = ang.cos().repeat_interleave(2, 1).contiguous(), ang.sin().repeat_interleave(2, 1).contiguous()
+    out = torch.empty(B * S, 3 * D, device="cuda", dtype=BF)
+    dense.linear(x, w, bias, out=out, epilogue=dense.EPI_QKV, rows_per_sample=S, text_rows=St, ln_q=lnq, ln_k=lnk, ln_eps=1e-6,
+                 rope=(cos, sin), model_dim=D)
+    y = F.linear(x.float(), w.float(), bias.float()).view(B, S, 3, H, 64)
+
+    def norm_rope(t, ln):
+        t = F.layer_norm(t, (64,), ln[0], ln[1], 1e-6)
+        vid = t[:, St:]                                               # [B, Sv, H, 64]
+        rot = torch.stack([-vid[..., 1::2], vid[..., 0::2]], dim=-1).flatten(-2)
+        vid = vid * cos[None, :, None, :] + rot * sin[None, :, None, :]
+        return torch.cat([t[:, :St], vid], dim=1)
+
+    ref = torch.stack([norm_rope(y[:, :, 0], lnq), norm_rope(y[:, :, 1], lnk), y[:, :, 2]], dim=2).reshape(B * S, 3 * D)
+    assert relerr(out, ref) < 1.5e-2                                 # bf16 roundings after the projection, the LayerNorm and at the store
 
 
 def test_attention_peaked_rows_rescale_path(lib):
