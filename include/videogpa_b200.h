@@ -25,8 +25,9 @@
 extern "C" {
 #endif
 
-#define VGPA_ABI_VERSION 3 /* 2: vgpa_attention_args gained `lse`; backward / training, T5 and transpose entry points added
-                              3: vgpa_attention_args gained `workspace` (bounded-softmax fast path of the head_dim-64 forward) */
+#define VGPA_ABI_VERSION 4 /* 2: vgpa_attention_args gained `lse`; backward / training, T5 and transpose entry points added
+                              3: vgpa_attention_args gained `workspace` (bounded-softmax fast path of the head_dim-64 forward)
+                              4: vgpa_conv3d_args gained the fused GroupNorm-statistics outputs (gn_*) */
 
 /* ------------------------------------------------------------------------------------------------
  * runtime
@@ -358,7 +359,15 @@ typedef struct vgpa_conv3d_args {
   void* out;            /* [T, H, W, ldo] bf16                                                       */
   int32_t T, H, W, Cin, Cout, Cout_pad, KT;
   int32_t ldo, ld_res;
+  /* Optional (ABI 4): GroupNorm statistics of the tensor being written, produced by the conv epilogue instead of a separate
+   * pass over it (the next CogVideoXSpatialNorm3D / GroupNorm normalises exactly this tensor). gn_mean_rstd [2, gn_groups]
+   * fp32 or NULL; gn_workspace >= vgpa_conv3d_gn_workspace_bytes(Cout), 16-byte aligned; Cout <= 512. */
+  float* gn_mean_rstd;
+  void* gn_workspace;
+  int32_t gn_groups;
+  float gn_eps;
 } vgpa_conv3d_args;
+size_t vgpa_conv3d_gn_workspace_bytes(int Cout);
 int vgpa_conv3d_causal_bf16(const vgpa_conv3d_args* args, void* stream);
 
 /* GroupNorm statistics over one [T, H, W, C] tensor (all of T, H, W: the statistics of one frame batch of one

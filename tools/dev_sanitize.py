@@ -64,5 +64,25 @@ gc = torch.Generator().manual_seed(1)
 batch = {"x_win": torch.randn(1, 16, 3, 16, 24, generator=gc), "x_lose": torch.randn(1, 16, 3, 16, 24, generator=gc),
          "prompt_emb": torch.randn(1, 18, 256, generator=gc).to(BF)}          # 2 x 306 tokens: not a multiple of 8, partial tiles everywhere
 step.training_step(batch).backward()
+# round-2 additions: exact attention kernel next to the bounded one (and a call whose heads split between them), the three-tier MVCS
+# kernel on an odd width, both T5 attention kernels (tensor-core path S <= 256, CUDA-core path above), 128-wide skinny GEMM tiles,
+# the re-scalable LoRA attachment, the temporal-patch (CogVideoX1.5) training forward + backward
+qq = torch.randn(1, 300, 128, device="cuda", generator=g).to(BF); kk = torch.randn(1, 261, 128, device="cuda", generator=g).to(BF)
+vv = torch.randn(1, 261, 128, device="cuda", generator=g).to(BF)
+dense.attention(qq, kk, vv, 2, exact=True)
+qq2 = qq.clone(); qq2[..., 64:] *= 40.0
+dense.attention(qq2, kk, vv, 2)
+depth_o = 2.0 + 0.5 * torch.rand(2, 3, 37, 57, device="cuda", generator=g)
+mvcs_batch(depth_o, K[None, :3].expand(2, 3, 3, 3).contiguous(), E[None, :3].expand(2, 3, 3, 4).contiguous())
+t5(torch.randint(0, 64, (1, 300), device="cuda", generator=g))
+dense.linear(torch.randn(226, 256, device="cuda", generator=g).to(BF), (torch.randn(128 * 80, 256, device="cuda", generator=g) * 0.05).to(BF), None)
+cfg15 = TransformerConfig(num_attention_heads=4, num_layers=1, text_embed_dim=256, sample_width=24, sample_height=16, sample_frames=9,
+                          max_text_seq_length=18, patch_size_t=2)
+m15 = CogVideoXTransformer3D.random_init(cfg15, seed=6, device="cuda")
+pol15 = LoRATrainableTransformer(m15, r=64, lora_alpha=128.0, gradient_checkpointing=True)
+step15 = DPOSharedStep(m15, None, beta=1.0, trainable=pol15)
+batch15 = {"x_win": torch.randn(1, 16, 5, 17, 25, generator=gc), "x_lose": torch.randn(1, 16, 5, 17, 25, generator=gc),
+           "prompt_emb": torch.randn(1, 18, 256, generator=gc).to(BF)}
+step15.training_step(batch15).backward()
 torch.cuda.synchronize()
 print("sanitize run complete")

@@ -100,6 +100,7 @@ class Conv3dArgs(C.Structure):
         ("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("residual", c_void_p), ("out", c_void_p),
         ("T", c_i32), ("H", c_i32), ("W", c_i32), ("Cin", c_i32), ("Cout", c_i32), ("Cout_pad", c_i32), ("KT", c_i32),
         ("ldo", c_i32), ("ld_res", c_i32),
+        ("gn_mean_rstd", c_void_p), ("gn_workspace", c_void_p), ("gn_groups", c_i32), ("gn_eps", C.c_float),
     ]
 
 
@@ -175,6 +176,7 @@ SIGNATURES = {
     "vgpa_t5_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_i64, c_void_p]),
     "vgpa_gated_mul_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p]),
     "vgpa_conv3d_causal_bf16": (c_int, [C.POINTER(Conv3dArgs), c_void_p]),
+    "vgpa_conv3d_gn_workspace_bytes": (C.c_size_t, [c_int]),
     "vgpa_groupnorm_workspace_bytes": (C.c_size_t, [c_int]),
     "vgpa_groupnorm_stats_bf16": (c_int, [c_void_p, c_i64, c_int, c_int, c_float, c_void_p, C.c_size_t, c_void_p, c_void_p]),
     "vgpa_spatialnorm_apply_bf16": (c_int, [C.POINTER(SpatialNormArgs), c_void_p]),
@@ -187,7 +189,7 @@ def lib_path() -> Path:
     return _LIB_PATH
 
 
-ABI_VERSION = 3          # VGPA_ABI_VERSION of include/videogpa_b200.h
+ABI_VERSION = 4          # VGPA_ABI_VERSION of include/videogpa_b200.h
 
 
 def load():

@@ -34,6 +34,8 @@ int  cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int num_sms();
+// vae_norm.cu: fold [nblocks][2][C] per-block channel sums / sums of squares into mean_rstd [2][groups] (fp64, fixed order)
+int launch_gn_finalize(const float* partial, int nblocks, int C, int groups, double count, float eps, float* mean_rstd, cudaStream_t stream);
 
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ float bf16_round(float x) {

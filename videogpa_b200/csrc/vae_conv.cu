@@ -26,6 +26,7 @@ constexpr int CV_TW = 16;       // tile width  (pixels)
 constexpr int CV_TH = 8;        // tile height (pixels)
 constexpr int CV_BK = 64;
 constexpr int CV_THREADS = 192;
+constexpr int CV_MAX_STATS_C = 512;   // widest layer whose GroupNorm statistics the epilogue can accumulate
 
 template <int BN>
 struct ConvCfg {
@@ -33,7 +34,8 @@ struct ConvCfg {
   static constexpr uint32_t A_BYTES = CV_BM * CV_BK * 2;
   static constexpr uint32_t B_BYTES = BN * CV_BK * 2;
   static constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
+  static constexpr uint32_t STATS_BYTES = 4 * 2 * CV_MAX_STATS_C * 4;   // per epilogue warp: [2][C] channel sums / sums of squares
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 + 256 + STATS_BYTES;
 };
 
 struct ConvParams {
@@ -43,7 +45,34 @@ struct ConvParams {
   int T, H, W, Cin, Cout, KT;
   int ldo, ld_res;
   int tiles_h, tiles_w, num_n;
+  float* stats_partial;   // [gridDim.x][2][Cout] per-CTA channel sums / sums of squares of the STORED (bf16) output, or NULL
 };
+
+// Sum over the 32 lanes of a warp of 16 per-lane values, 16 shuffles instead of 80: every step exchanges the half a lane does
+// not keep. Afterwards lane l holds the total of value index ((l >> 1) & 15) (lanes l and l ^ 1 hold the same total).
+__device__ __forceinline__ float warp_transpose_sum16(const float (&a)[16], int lane) {
+  float b[8], c[4], d[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h16 ? a[8 + i] : a[i], send = h16 ? a[i] : a[8 + i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h8 ? b[4 + i] : b[i], send = h8 ? b[i] : b[4 + i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h4 ? c[2 + i] : c[i], send = h4 ? c[i] : c[2 + i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float keep = h2 ? d[1] : d[0], send = h2 ? d[0] : d[1];
+  float e = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  e += __shfl_xor_sync(0xffffffffu, e, 1);
+  return e;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(CV_THREADS, 1)
@@ -59,9 +88,12 @@ vae_conv3d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + 256);   // [4][2][Cout]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (p.stats_partial != nullptr)
+    for (int i = threadIdx.x; i < 4 * 2 * p.Cout; i += CV_THREADS) s_stats[i] = 0.f;
   const int tiles_per_frame = p.tiles_h * p.tiles_w;
   const int num_m = p.T * tiles_per_frame;
   const int num_tiles = num_m * p.num_n;
@@ -171,8 +203,10 @@ vae_conv3d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::tmem_ld_32x16(t_row + c0, acc);
         ptx::tmem_ld_wait();
         const int col = n_blk * BN + c0;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
         if (live && col < p.Cout) {
-          float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
           if (p.bias != nullptr) {
@@ -207,6 +241,20 @@ vae_conv3d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           op[0] = o0;
           op[1] = o1;
         }
+        if (p.stats_partial != nullptr && col < p.Cout) {        // warp-uniform: every lane takes part in the shuffles
+          // GroupNorm statistics of the tensor being written (what the next SpatialNorm normalises with): per-channel sum and
+          // sum of squares of the bf16 values as stored; pixels outside the image contribute zeros. Each epilogue warp owns
+          // a [2][Cout] slice in shared memory, added to in tile order: deterministic.
+          float sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] = bf16_round(v[i]); sq[i] = v[i] * v[i]; }
+          const float ts = warp_transpose_sum16(v, lane), tq = warp_transpose_sum16(sq, lane);
+          if ((lane & 1) == 0) {
+            float* st = s_stats + quarter * 2 * p.Cout + col + (lane >> 1);
+            st[0] += ts;
+            st[p.Cout] += tq;
+          }
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -218,10 +266,17 @@ vae_conv3d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (p.stats_partial != nullptr) {
+    const int n2 = 2 * p.Cout;
+    for (int i = threadIdx.x; i < n2; i += CV_THREADS)
+      p.stats_partial[static_cast<long long>(blockIdx.x) * n2 + i] = ((s_stats[i] + s_stats[n2 + i]) + s_stats[2 * n2 + i]) + s_stats[3 * n2 + i];
+  }
 }
 
+struct GnOut { float* mean_rstd; int groups; float eps; };
+
 template <int BN>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, const GnOut& gn, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -232,11 +287,20 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams
   const int grid = num_tiles < num_sms() ? static_cast<int>(num_tiles) : num_sms();
   vae_conv3d_kernel<BN><<<grid, CV_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   VGPA_LAUNCH_CHECK("vae_conv3d_kernel");
+  if (p.stats_partial != nullptr) {
+    // fold the per-CTA partials in fp64 in a fixed order and reduce channels to groups (vae_norm.cu)
+    return launch_gn_finalize(p.stats_partial, grid, p.Cout, gn.groups, static_cast<double>(p.T) * p.H * p.W * (p.Cout / gn.groups), gn.eps,
+                              gn.mean_rstd, stream);
+  }
   return 0;
 }
 
 }  // namespace
 }  // namespace vgpa
+
+extern "C" size_t vgpa_conv3d_gn_workspace_bytes(int Cout) {
+  return static_cast<size_t>(vgpa::num_sms() > 0 ? vgpa::num_sms() : 148) * 2 * (Cout > 0 ? Cout : 0) * sizeof(float) + 256;
+}
 
 extern "C" int vgpa_conv3d_causal_bf16(const vgpa_conv3d_args* a, void* stream) {
   using namespace vgpa;
@@ -292,11 +356,20 @@ extern "C" int vgpa_conv3d_causal_bf16(const vgpa_conv3d_args* a, void* stream) 
   p.tiles_h = (a->H + CV_TH - 1) / CV_TH;
   p.tiles_w = (a->W + CV_TW - 1) / CV_TW;
   p.num_n = a->Cout_pad / BN;
+  p.stats_partial = nullptr;
+  GnOut gn{a->gn_mean_rstd, a->gn_groups, a->gn_eps};
+  if (a->gn_mean_rstd != nullptr) {
+    VGPA_CHECK(a->gn_workspace != nullptr && (reinterpret_cast<uintptr_t>(a->gn_workspace) & 15) == 0, "vgpa_conv3d_causal_bf16: gn_workspace missing or misaligned");
+    VGPA_CHECK(a->Cout_pad != 16 && a->Cout <= CV_MAX_STATS_C && a->gn_groups > 0 && a->gn_groups <= 64 && a->Cout % a->gn_groups == 0,
+               "vgpa_conv3d_causal_bf16: fused GroupNorm statistics need Cout <= %d divisible into gn_groups (Cout=%d groups=%d)", CV_MAX_STATS_C,
+               a->Cout, a->gn_groups);
+    p.stats_partial = static_cast<float*>(a->gn_workspace);
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (BN) {
-    case 256: return launch_conv<256>(tmA, tmB, p, s);
-    case 128: return launch_conv<128>(tmA, tmB, p, s);
-    case 64: return launch_conv<64>(tmA, tmB, p, s);
-    default: return launch_conv<16>(tmA, tmB, p, s);
+    case 256: return launch_conv<256>(tmA, tmB, p, gn, s);
+    case 128: return launch_conv<128>(tmA, tmB, p, gn, s);
+    case 64: return launch_conv<64>(tmA, tmB, p, gn, s);
+    default: return launch_conv<16>(tmA, tmB, p, gn, s);
   }
 }

@@ -288,6 +288,14 @@ extern "C" size_t vgpa_groupnorm_workspace_bytes(int C) {
   return static_cast<size_t>(vgpa::GN_MAX_BLOCKS) * 2 * static_cast<size_t>(C > 0 ? C : 0) * sizeof(float);
 }
 
+namespace vgpa {
+int launch_gn_finalize(const float* partial, int nblocks, int C, int groups, double count, float eps, float* mean_rstd, cudaStream_t stream) {
+  gn_finalize_kernel<<<groups, 256, 0, stream>>>(partial, nblocks, C, groups, count, eps, mean_rstd);
+  VGPA_LAUNCH_CHECK("gn_finalize_kernel");
+  return 0;
+}
+}  // namespace vgpa
+
 extern "C" int vgpa_groupnorm_stats_bf16(const void* x, int64_t n_pixels, int C, int groups, float eps, void* workspace,
                                          size_t workspace_bytes, float* mean_rstd, void* stream) {
   using namespace vgpa;

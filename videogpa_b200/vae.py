@@ -78,6 +78,8 @@ class AutoencoderKLCogVideoXDecoder:
         self._streams = None
         self.use_cuda_graph = False
         self._graphs = {}
+        self.fuse_gn_stats = True        # GroupNorm statistics from the conv epilogues (False: separate two-kernel pass per norm)
+        self._ws_conv = None
         self._capturing = False
         c = self.config
         self.rc = tuple(reversed(c.block_out_channels))
@@ -267,12 +269,14 @@ class AutoencoderKLCogVideoXDecoder:
             return [0] + rest
         return [int(math.floor(k * (Tz / T))) for k in range(T)]
 
-    def _snorm_apply(self, x, norm: _SNorm, yb, zshape, out, silu: bool):
-        """x [T,H,W,C] -> out (same shape, may be a view 2 frames into a time-padded buffer)."""
+    def _snorm_apply(self, x, norm: _SNorm, yb, zshape, out, silu: bool, stats=None):
+        """x [T,H,W,C] -> out (same shape, may be a view 2 frames into a time-padded buffer). `stats` = the GroupNorm
+        mean / rstd of x when the conv that wrote x already produced them in its epilogue."""
         lib = _lib.load()
         T, H, W, C_ = x.shape
         Tz, Hz, Wz = zshape
-        stats = self._gn_stats(x, C_)
+        if stats is None:
+            stats = self._gn_stats(x, C_)
         a = SpatialNormArgs()
         a.x, a.out, a.mean_rstd = x.data_ptr(), out.data_ptr(), stats.data_ptr()
         a.gamma, a.beta = norm.gamma.data_ptr(), norm.beta.data_ptr()
@@ -291,7 +295,9 @@ class AutoencoderKLCogVideoXDecoder:
         a.silu = 1 if silu else 0
         _lib.check(lib.vgpa_spatialnorm_apply_bf16(C.byref(a), _lib.current_stream()), "vgpa_spatialnorm_apply_bf16")
 
-    def _conv_call(self, cv: _Conv, xpad: torch.Tensor, T: int, out: torch.Tensor | None = None, residual=None) -> torch.Tensor:
+    def _conv_call(self, cv: _Conv, xpad: torch.Tensor, T: int, out: torch.Tensor | None = None, residual=None, want_stats: bool = False):
+        """-> out, or (out, mean_rstd [2 * groups] fp32) with want_stats: the GroupNorm statistics of `out`, accumulated by the
+        conv epilogue (no separate pass over the tensor that the next norm would otherwise read once more)."""
         lib = _lib.load()
         Tp, H, W, Cin = xpad.shape
         if Tp != T + cv.kt - 1 or Cin != cv.cin:
@@ -305,7 +311,21 @@ class AutoencoderKLCogVideoXDecoder:
         a.T, a.H, a.W, a.Cin, a.Cout, a.Cout_pad, a.KT = T, H, W, Cin, cv.cout, cv.cout_pad, cv.kt
         a.ldo = ldo
         a.ld_res = residual.shape[-1] if residual is not None else 0
+        stats = None
+        if want_stats and self.fuse_gn_stats and cv.cout_pad != 16 and cv.cout <= 512:
+            need = lib.vgpa_conv3d_gn_workspace_bytes(cv.cout)
+            if self._ws_conv is None:
+                self._ws_conv = {}
+            key = torch.cuda.current_stream().cuda_stream        # one scratch buffer per stream: tiles decode concurrently
+            ws = self._ws_conv.get(key)
+            if ws is None or ws.numel() < need:
+                ws = self._ws_conv[key] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=self.device)
+            stats = torch.empty(2 * self.config.norm_num_groups, dtype=torch.float32, device=self.device)
+            a.gn_mean_rstd, a.gn_workspace = stats.data_ptr(), ws.data_ptr()
+            a.gn_groups, a.gn_eps = self.config.norm_num_groups, 1e-6
         _lib.check(lib.vgpa_conv3d_causal_bf16(C.byref(a), _lib.current_stream()), "vgpa_conv3d_causal_bf16")
+        if want_stats:
+            return out, stats
         return out
 
     def _finish_timepad(self, buf: torch.Tensor, key: str, cache_in: dict | None, cache_out: dict):
@@ -318,21 +338,25 @@ class AutoencoderKLCogVideoXDecoder:
             buf[1].copy_(buf[2])
         cache_out[key] = buf[-2:].clone()
 
-    def _norm_conv(self, x, norm, cv, key, yb, zshape, cache_in, cache_out, residual=None, out=None):
-        """SpatialNorm -> SiLU -> causal conv (the repeated unit of CogVideoXResnetBlock3D and the output head)."""
+    def _norm_conv(self, x, norm, cv, key, yb, zshape, cache_in, cache_out, residual=None, out=None, x_stats=None, want_stats=False):
+        """SpatialNorm -> SiLU -> causal conv (the repeated unit of CogVideoXResnetBlock3D and the output head). x_stats: the
+        GroupNorm statistics of x if its producer made them; want_stats: also return those of the result."""
         T, H, W, C_ = x.shape
         buf = torch.empty((T + 2, H, W, C_), dtype=BF16, device=self.device)
-        self._snorm_apply(x, norm, yb, zshape, buf[2:], silu=True)
+        self._snorm_apply(x, norm, yb, zshape, buf[2:], silu=True, stats=x_stats)
         self._finish_timepad(buf, key, cache_in, cache_out)
-        return self._conv_call(cv, buf, T, out=out, residual=residual)
+        return self._conv_call(cv, buf, T, out=out, residual=residual, want_stats=want_stats)
 
-    def _resnet_fwd(self, r, x, key, yb, zshape, cache_in, cache_out):
+    def _resnet_fwd(self, r, x, key, yb, zshape, cache_in, cache_out, x_stats=None):
+        """-> (block output, its GroupNorm statistics): every tensor a norm reads is written by a conv epilogue that also
+        accumulates its statistics (conv1 -> norm2, conv2 + residual -> the next block's norm1)."""
         T, H, W, _ = x.shape
-        h = self._norm_conv(x, r.norm1, r.conv1, key + ".conv1", yb, zshape, cache_in, cache_out)
+        h, h_stats = self._norm_conv(x, r.norm1, r.conv1, key + ".conv1", yb, zshape, cache_in, cache_out, x_stats=x_stats, want_stats=True)
         res = x
         if r.sc_w is not None:
             res = dense.linear(x.view(-1, r.ci), r.sc_w, r.sc_b).view(T, H, W, r.co)
-        return self._norm_conv(h, r.norm2, r.conv2, key + ".conv2", yb, zshape, cache_in, cache_out, residual=res)
+        return self._norm_conv(h, r.norm2, r.conv2, key + ".conv2", yb, zshape, cache_in, cache_out, residual=res, x_stats=h_stats,
+                               want_stats=True)
 
     def _upsample_fwd(self, blk, x):
         lib = _lib.load()
@@ -348,7 +372,7 @@ class AutoencoderKLCogVideoXDecoder:
         arr = (C.c_int32 * 16)(*(t_src + [0] * (16 - To)))
         _lib.check(lib.vgpa_upsample_nearest_bf16(x.data_ptr(), up.data_ptr(), To, H, W, C_, arr, _lib.current_stream()),
                    "vgpa_upsample_nearest_bf16")
-        return self._conv_call(blk.upsample, up, To)
+        return self._conv_call(blk.upsample, up, To, want_stats=True)
 
     # ------------------------------------------------------------------ one decoder pass over one frame batch of one tile
     def _decoder_pass(self, zt: torch.Tensor, cache_in: dict | None, out: torch.Tensor):
@@ -360,17 +384,17 @@ class AutoencoderKLCogVideoXDecoder:
         buf = torch.empty((Tz + 2, hz, wz, self.zc_pad), dtype=BF16, device=self.device)
         buf[2:].copy_(zt)
         self._finish_timepad(buf, "conv_in", cache_in, cache_out)
-        h = self._conv_call(self.conv_in, buf, Tz)
+        h, st = self._conv_call(self.conv_in, buf, Tz, want_stats=True)
         for j, r in enumerate(self.mid):
-            h = self._resnet_fwd(r, h, f"mid.{j}", yb, zshape, cache_in, cache_out)
+            h, st = self._resnet_fwd(r, h, f"mid.{j}", yb, zshape, cache_in, cache_out, x_stats=st)
         for i, blk in enumerate(self.up):
             for j, r in enumerate(blk.resnets):
-                h = self._resnet_fwd(r, h, f"up.{i}.{j}", yb, zshape, cache_in, cache_out)
+                h, st = self._resnet_fwd(r, h, f"up.{i}.{j}", yb, zshape, cache_in, cache_out, x_stats=st)
             if blk.upsample is not None:
-                h = self._upsample_fwd(blk, h)
+                h, st = self._upsample_fwd(blk, h)
         if tuple(out.shape[:3]) != tuple(h.shape[:3]):
             raise RuntimeError(f"decoder pass produced {tuple(h.shape)}, expected {tuple(out.shape)}")
-        self._norm_conv(h, self.norm_out, self.conv_out, "conv_out", yb, zshape, cache_in, cache_out, out=out)
+        self._norm_conv(h, self.norm_out, self.conv_out, "conv_out", yb, zshape, cache_in, cache_out, out=out, x_stats=st)
         return cache_out
 
     @staticmethod
