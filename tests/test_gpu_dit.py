@@ -21,8 +21,11 @@ def relerr(a, b):
     return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 64, 192), (1000, 768, 3072), (226, 3072, 4096), (17776, 3072, 3072)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 64, 192), (1000, 768, 3072), (226, 3072, 4096), (17776, 3072, 3072),
+                                   (226, 10240, 512), (226, 12288, 512), (130, 1280, 256), (226, 2560, 320)])
 def test_gemm_bias(lib, M, N, K):
+    """The last four shapes are skinny problems whose tile width is chosen per shape: 160 (64 x 160 = 10 240, with its 32-column
+    tail group), 192 (64 x 192 = 12 288) and 64 for the two small ones."""
     from videogpa_b200 import dense
     torch.manual_seed(M + N + K)
     a = (torch.randn(M, K, device="cuda") * 0.5).to(BF)
@@ -50,6 +53,21 @@ def test_attention(lib, B, H, S, Skv):
     ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, S, D)
     assert torch.isfinite(out.float()).all()
     assert relerr(out, ref) < 1e-2                                   # P is rounded to bf16 before PV, output to bf16
+
+
+@pytest.mark.parametrize("N", [10240, 12288, 4096])
+def test_gemm_gated_residual_skinny_tiles(lib, N):
+    """x <- x + gate * y (in place, eager-bf16 roundings) on the tile widths the skinny dispatcher picks (160 / 192 / 64)."""
+    from videogpa_b200 import dense
+    torch.manual_seed(N)
+    M, K = 226, 384
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(BF)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(BF)
+    b = (torch.randn(N, device="cuda") * 0.1).to(BF)
+    x = torch.randn(M, N, device="cuda").to(BF)
+    ref = x.float() + (a.float() @ w.float().t() + b.float()).to(BF).float()          # gate pointers NULL = 1
+    dense.linear(a, w, b, out=x, epilogue=dense.EPI_GATE_RES)
+    assert relerr(x, ref) < 6e-3
 
 
 def test_attention_exact_kernel_and_mixed_heads(lib):

@@ -49,10 +49,10 @@ struct EpiParams {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN > 128 ? 5 : 6);
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);   // allocations are powers of two
   static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256;
 };
 
@@ -64,15 +64,17 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
-// Epilogue over one 64-column group held in v[64] for output row `row` (may be >= M: no stores).
-template <int EPI>
+// Epilogue over one 64-column group held in v[64] for output row `row` (may be >= M: no stores). NC = 32: only the first 32
+// columns are valid (the tail group of a 160-wide tile).
+template <int EPI, int NC = 64>
 __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0, int M,
                                                const EpiParams& ep, const uint4 (&res)[8]) {
+  static_assert(NC == 64 || (EPI != VGPA_EPI_QKV && EPI != VGPA_EPI_GATE_RES_F32), "the per-head QKV / fp32-residual epilogues work on whole 64-column groups");
   const bool live = row < M;
   if (ep.bias != nullptr) {
     const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + col0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NC / 8; ++i) {
       const uint4 b = __ldg(bp + i);
       const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z),
                    b3 = unpack_bf16x2(b.w);
@@ -84,7 +86,7 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
 
   if constexpr (EPI == VGPA_EPI_BIAS_GELU) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(bf16_round(v[i]));
+    for (int i = 0; i < NC; ++i) v[i] = gelu_tanh(bf16_round(v[i]));
   } else if constexpr (EPI == VGPA_EPI_GATE_RES) {
     // x <- x + gate * y with eager-bf16 roundings (y, gate*y, sum each rounded to bf16)
     int srow = row, b = 0;
@@ -93,7 +95,7 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
     if (live) {
       const uint4* gp = (g != nullptr) ? reinterpret_cast<const uint4*>(g + b * ep.gate_stride_b + col0) : nullptr;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < NC / 8; ++i) {
         const uint4 r = res[i];                          // residual row chunk, prefetched one column group ahead
         uint4 gg = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0
         if (gp != nullptr) gg = __ldg(gp + i);
@@ -137,7 +139,7 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
     if (live) {
       const uint4* rp = reinterpret_cast<const uint4*>(orow);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < NC / 8; ++i) {
         const uint4 r = rp[i];
         const uint32_t ru[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -193,7 +195,7 @@ __device__ __forceinline__ void epilogue_group(float (&v)[64], int row, int col0
   if (live) {
     uint4* op = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NC / 8; ++i) {
       uint4 o;
       o.x = pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
       o.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
@@ -337,8 +339,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto load_res = [&](int g, uint4 (&dst)[8]) {
         if constexpr (EPI == VGPA_EPI_GATE_RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(ep.out + static_cast<size_t>(row < M ? row : 0) * ep.ldo + n_blk * BN + g * 64);
+          const int nv = (BN - g * 64 >= 64) ? 8 : (BN - g * 64) / 8;      // the tail group of a 160-wide tile has 32 columns
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = rp[i];
+          for (int i = 0; i < 8; ++i) if (i < nv) dst[i] = rp[i];
         }
       };
       load_res(0, res);
@@ -347,7 +350,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int g = 0; g < BN / 64; ++g) {
         uint4 nxt[8];
-        if (g + 1 < BN / 64) load_res(g + 1, nxt);
+        if (g + 1 < (BN + 63) / 64) load_res(g + 1, nxt);
         uint32_t r0[32], r1[32];
         ptx::tmem_ld_32x32(t_row + g * 64, r0);
         ptx::tmem_ld_32x32(t_row + g * 64 + 32, r1);
@@ -360,6 +363,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 8; ++i) res[i] = nxt[i];
         }
+      }
+      if constexpr (BN % 64 != 0) {                       // 32-column tail group of a 160-wide tile
+        constexpr int g = BN / 64;
+        uint32_t r0[32];
+        ptx::tmem_ld_32x32(t_row + g * 64, r0);
+        ptx::tmem_ld_wait();
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = 0.f; }
+        epilogue_group<EPI, 32>(v, row, n_blk * BN + g * 64, M, ep, res);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -420,14 +433,27 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
              "vgpa_linear_bf16: pointers must be 16-byte aligned");
   int BN = (a->N % 256 == 0) ? 256 : 64;
-  // skinny problems (T5 prompt encoder: M = 226) are bound by streaming W once from HBM: with 128x256 tiles fewer CTAs
-  // than SMs would be pulling it, so use narrower tiles there. Every tile also re-fetches its 128-row activation tile from
-  // L2, which is 2/3 of an SM's ingest at BN = 64 and 1/2 at BN = 128: take 128 whenever that still gives ~one tile per SM
-  // (T5: the fused q|k|v and the wi projections), 64 otherwise (N = 4096: o and wo).
-  if (BN == 256 && static_cast<long long>((a->M + BM - 1) / BM) * (a->N / 256) < 148) {
-    static int k_bn128 = -1;
-    if (k_bn128 < 0) { const char* e = getenv("VGPA_GEMM_BN128"); k_bn128 = e ? atoi(e) : 1; }
-    BN = (k_bn128 && a->N % 128 == 0 && static_cast<long long>((a->M + BM - 1) / BM) * (a->N / 128) >= 120) ? 128 : 64;
+  // Skinny problems (T5 prompt encoder: M = 226) are bound by streaming W once from HBM, and what limits that stream is each SM's
+  // ingest from L2 (~106 GB/s measured): a tile moves A (16 KB) + W (BN / 8 KB) per 64-deep k block and only the W part is new
+  // data, and a tile count just above the SM count costs a whole second wave (N = 10 240 at BN = 128: 160 tiles on 148 SMs).
+  // Pick the tile width that minimises waves x bytes per k block among the widths that divide N; 160 and 192 exist for the
+  // epilogues the skinny callers use (bias, bias + GELU, gated residual): 10 240 = 64 x 160 and 12 288 = 64 x 192 are one wave.
+  const long long m_tiles = (a->M + BM - 1) / BM;
+  if (BN == 256 && m_tiles * (a->N / 256) < 148) {
+    static int k_wide = -1;
+    if (k_wide < 0) { const char* e = getenv("VGPA_GEMM_SKINNY_TILES"); k_wide = e ? atoi(e) : 1; }   // dev: 0 = 64-wide tiles only
+    const bool odd_ok = a->epilogue == VGPA_EPI_BIAS || a->epilogue == VGPA_EPI_BIAS_GELU || a->epilogue == VGPA_EPI_GATE_RES;
+    const int cand[5] = {256, 192, 160, 128, 64};
+    double best = 1e30;
+    BN = 64;
+    for (int c = 0; c < 5; ++c) {
+      const int bn = cand[c];
+      if (a->N % bn != 0 || (!k_wide && bn != 64) || ((bn == 160 || bn == 192) && !odd_ok)) continue;
+      const long long tiles = m_tiles * (a->N / bn);
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      const double t = static_cast<double>(waves) * (16.0 + bn / 8.0);        // KB per k block of a tile x tiles an SM runs in sequence
+      if (t < best) { best = t; BN = bn; }
+    }
   }
   // cluster of 2 with W-tile multicast for the big GEMMs (development knob VGPA_GEMM_CLUSTER=0 turns it off)
   static int use_cluster = -1;
@@ -501,6 +527,21 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
                                 : launch_gemm<256, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s))   \
            : BN == 128 ? launch_gemm<128, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s)             \
                        : launch_gemm<64, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s);
+#define VGPA_GEMM_DISPATCH_ODD(EPI)                                                      \
+  case EPI:                                                                              \
+    return BN == 192 ? launch_gemm<192, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s)      \
+                     : launch_gemm<160, EPI, 1>(tmA, tmB, a->M, a->N, a->K, ep, s);
+  if (BN == 160 || BN == 192) {
+    switch (a->epilogue) {
+      VGPA_GEMM_DISPATCH_ODD(VGPA_EPI_BIAS)
+      VGPA_GEMM_DISPATCH_ODD(VGPA_EPI_BIAS_GELU)
+      VGPA_GEMM_DISPATCH_ODD(VGPA_EPI_GATE_RES)
+      default:
+        break;
+    }
+    set_error("vgpa_linear_bf16: tile width %d is not instantiated for epilogue %d", BN, a->epilogue);
+    return 1;
+  }
   switch (a->epilogue) {
     VGPA_GEMM_DISPATCH(VGPA_EPI_BIAS)
     VGPA_GEMM_DISPATCH(VGPA_EPI_BIAS_GELU)
@@ -512,6 +553,7 @@ extern "C" int vgpa_linear_bf16(const vgpa_linear_args* a, void* stream) {
       break;
   }
 #undef VGPA_GEMM_DISPATCH
+#undef VGPA_GEMM_DISPATCH_ODD
   set_error("vgpa_linear_bf16: unknown epilogue %d", a->epilogue);
   return 1;
 }
