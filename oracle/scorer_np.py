@@ -306,7 +306,7 @@ def unproject_depth(depth, intrinsics, extrinsics_w2c):
 
 
 # ------------------------------------------------------------------------------------------------
-# a-11  8-point fundamental matrix + Sampson       reference: metrics/epipolar.py:194-216 -> kornia (App. A.6) [UNPINNED]
+# a-11  8-point fundamental matrix + Sampson       reference: metrics/epipolar.py:194-216 -> kornia (App. A.6) [kornia absent; pinned to OpenCV's FM_8POINT / sampsonDistance, tests/test_oracle_golden.py]
 # ------------------------------------------------------------------------------------------------
 def _normalize_points(p):
     mu = p.mean(axis=0)

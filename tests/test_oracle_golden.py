@@ -108,3 +108,32 @@ def test_epipolar_geometry_selfcheck():
     noisy = p2 + rng.normal(0, 0.5, p2.shape)
     assert 0.05 < o.sampson_mean_distance(o.find_fundamental(p1, noisy), p1, noisy) < 1.0
     assert o.epipolar_metric_from_matches([None, (p1[:5], p2[:5])]) == -1.0
+
+
+def test_epipolar_oracle_vs_opencv():
+    """kornia (the library behind metrics/epipolar.py:194-216) is not installable here, but OpenCV — which the reference also imports —
+    ships independent implementations of the same two published algorithms: `cv2.findFundamentalMat(..., FM_8POINT)` (Hartley's
+    normalised 8-point: isotropic normalisation, least squares, rank-2 projection) and `cv2.sampsonDistance` (the squared first-order
+    geometric error). The oracle's restatement of kornia's `find_fundamental` / `sampson_epipolar_distance` must agree with them:
+    F up to scale and sign to 1e-6, the mean distance sqrt(d^2 + 1e-8) to 1e-5."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for p, n in enumerate([300, 120, 64, 30, 9]):
+        X = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(3, 6, n)], 1)
+        ang = math.radians(2.0 + p)
+        R = np.array([[math.cos(ang), 0, math.sin(ang)], [0, 1, 0], [-math.sin(ang), 0, math.cos(ang)]])
+        t = np.array([0.2, 0.01 * p, 0.02])
+        K = np.array([[200.0, 0, 128], [0, 200.0, 128], [0, 0, 1.0]])
+        p1 = (K @ X.T).T; p1 = (p1[:, :2] / p1[:, 2:]).astype(np.float32)
+        X2 = (R @ X.T).T + t
+        p2 = (K @ X2.T).T; p2 = (p2[:, :2] / p2[:, 2:] + rng.normal(0, 0.4, (n, 2))).astype(np.float32)
+        F = o.find_fundamental(p1, p2).astype(np.float64)
+        Fc, _ = cv2.findFundamentalMat(p1.astype(np.float64), p2.astype(np.float64), cv2.FM_8POINT)
+        Fn, Fcn = F / np.linalg.norm(F), Fc / np.linalg.norm(Fc)
+        if np.sum(Fn * Fcn) < 0:
+            Fcn = -Fcn
+        assert np.abs(Fn - Fcn).max() < 1e-6, (n, np.abs(Fn - Fcn).max())
+        d2 = [cv2.sampsonDistance(np.array([a[0], a[1], 1.0]), np.array([b[0], b[1], 1.0]), F)
+              for a, b in zip(p1.astype(np.float64), p2.astype(np.float64))]
+        d_cv = float(np.mean(np.sqrt(np.array(d2) + 1e-8)))
+        assert abs(o.sampson_mean_distance(F, p1, p2) - d_cv) < 1e-5 * max(d_cv, 1.0), (n, d_cv)
