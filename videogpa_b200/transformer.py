@@ -317,8 +317,10 @@ class CogVideoXTransformer3D:
         return L * (lin + attn) + embed
 
     def kernel_launches(self, B: int, num_layers: int | None = None) -> int:
+        """Kernels of this library launched by one forward: per block 2 modulation linears, 2 LayerNorm-modulate, 4 GEMMs and the
+        attention call's 3 kernels (|q|,|k| bound pre-pass, bounded-softmax kernel, exact kernel for the heads above the bound)."""
         L = self.config.num_layers if num_layers is None else num_layers
-        return 3 + 1 + 2 * B + 9 * L + 3 + B + 1
+        return 3 + 1 + 2 * B + 11 * L + 3 + B + 1
 
     def config_dict(self) -> dict:
         return asdict(self.config)
