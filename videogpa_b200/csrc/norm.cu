@@ -32,8 +32,10 @@ struct LnParams {
 // VPL = uint4 vectors per lane (D = VPL * 256)
 // XF32: x is the fp32 residual stream of the Wan2.2 forward; everything up to the single bf16 rounding of the output is fp32
 // (torch.autocast semantics). Otherwise x is bf16 and the modulation follows torch's eager-bf16 roundings.
+// Two CTAs per SM up to D = 3072 (VPL 12): the bf16 row kernel needed 130 registers, two more than lets a second 256-thread CTA
+// onto the SM, and the kernel is bound by the rows it keeps in flight (8 warps = 8 rows = 48 KB per SM is half of what HBM needs).
 template <int VPL, bool XF32>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, (VPL <= 12 && !XF32) ? 2 : 1)
 ln_modulate_kernel(LnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
