@@ -24,7 +24,7 @@ struct RnParams {
 
 // VPL = uint4 vectors per lane (D = VPL * 256)
 template <int VPL>
-__global__ void __launch_bounds__(RN_WARPS * 32)
+__global__ void __launch_bounds__(RN_WARPS * 32, (VPL <= 12) ? 2 : 1)   // 144 registers at VPL 12 kept a second CTA off the SM (cf. ln_modulate_kernel)
 rmsnorm_rope_kernel(RnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * RN_WARPS + warp;
