@@ -41,15 +41,16 @@ def resolve_image(item: dict, base_dir: str | None) -> str:
     return image_path
 
 
-def load_image_tensor(image_path: str, height: int, width: int) -> torch.Tensor:
+def load_image_tensor(image_path, height: int, width: int) -> torch.Tensor:
     """diffusers `load_image` + VideoProcessor.preprocess: RGB, resized to (width, height) (lanczos), [-1, 1], [3, H, W]."""
     import numpy as np
     from PIL import Image
-    img = Image.open(image_path).convert("RGB").resize((width, height), Image.LANCZOS)
+    img = image_path if hasattr(image_path, "resize") else Image.open(image_path)          # a path or an already loaded PIL image
+    img = img.convert("RGB").resize((width, height), Image.LANCZOS)
     return torch.from_numpy(np.asarray(img).copy()).permute(2, 0, 1).float() / 127.5 - 1.0
 
 
-def first_frame_latent(image_path: str, shape, device, encoder, scaling_factor: float, generator=None,
+def first_frame_latent(image_path, shape, device, encoder, scaling_factor: float, generator=None,
                        height: int | None = None, width: int | None = None) -> torch.Tensor:
     """-> image latents [1, F, 16, h, w]: the encoded first frame followed by F-1 zero frames (App. A.4)."""
     F_, C, h, w = shape
