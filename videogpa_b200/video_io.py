@@ -26,19 +26,34 @@ def center_crop_and_resize(frame: np.ndarray, size: int = 518) -> np.ndarray:
     return cv2.resize(frame[top:top + side, left:left + side], (size, size), interpolation=cv2.INTER_LINEAR)
 
 
-def count_frames(video_path: str) -> int:
-    """Number of decodable frames (the container's frame count can be off by a few, so a mismatch falls back to decoding)."""
+def count_frames(video_path: str, decode: bool = False) -> int:
+    """Number of frames: the container's count, or (decode=True, or when the container reports none) the number that actually
+    decodes — `len(VideoReader(...))` of the reference is the decodable count."""
     import cv2
     cap = cv2.VideoCapture(str(video_path))
     if not cap.isOpened():
         raise RuntimeError(f"cannot read video {video_path}")
-    n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    n = 0 if decode else int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
     if n <= 0:
         n = 0
         while cap.grab():
             n += 1
     cap.release()
     return n
+
+
+def _read_sampled(video_path: str, index_rule) -> np.ndarray:
+    """Frames at `index_rule(total)`; if the container over-reports its length the indices are re-derived from the decodable count."""
+    total = count_frames(video_path)
+    if total <= 0:
+        raise RuntimeError(f"Video has 0 frames: {video_path}")
+    try:
+        return read_frames(video_path, index_rule(total))
+    except RuntimeError:
+        decodable = count_frames(video_path, decode=True)
+        if decodable <= 0 or decodable == total:
+            raise
+        return read_frames(video_path, index_rule(decodable))
 
 
 def read_frames(video_path: str, indices) -> np.ndarray:
@@ -70,10 +85,7 @@ def read_frames(video_path: str, indices) -> np.ndarray:
 def sample_uniform_frames(video_path: str, n_frames: int = 48, size: int = 518) -> np.ndarray:
     """utils/video_utils.py:20-45 -> `[T, size, size, 3]` uint8 RGB; the `frame_sampler` of process_video.VideoProcessor."""
     from .metrics import sample_frame_indices
-    total = count_frames(video_path)
-    if total <= 0:
-        raise RuntimeError(f"Video has 0 frames: {video_path}")
-    frames = read_frames(video_path, sample_frame_indices(total, n_frames))
+    frames = _read_sampled(video_path, lambda total: sample_frame_indices(total, n_frames))
     return np.stack([center_crop_and_resize(f, size) for f in frames], axis=0)
 
 
@@ -81,8 +93,7 @@ def load_video_frames_tensor(video_path: str, num_frames: int = 49, device=None)
     """train/CogVideoX-5B/02_encode.py:55-63 -> float `[3, T, H, W]` in [0, 1] (every frame of a clip shorter than
     `num_frames`); the input of encode.encode_video_latent."""
     from .encode import select_frame_indices
-    total = count_frames(video_path)
-    frames = read_frames(video_path, select_frame_indices(total, num_frames))
+    frames = _read_sampled(video_path, lambda total: select_frame_indices(total, num_frames))
     t = torch.from_numpy(frames).float() / 255.0
     t = t.permute(3, 0, 1, 2)
     return t.to(device) if device is not None else t
