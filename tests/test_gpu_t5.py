@@ -57,6 +57,57 @@ def test_t5_encoder_vs_transformers(lib, B, S):
     assert (got - ref).abs().mean().item() < 5e-3 * ref.abs().max().item()
 
 
+def test_umt5_encoder_vs_transformers(lib):
+    """umT5 (the text encoder of Wan2.2: one relative-position table per block) against transformers' UMT5EncoderModel, without a mask
+    and with Wan's padded-prompt-plus-mask call: the rows of the real tokens must match, padded rows come back as zeros."""
+    from transformers import UMT5Config, UMT5EncoderModel
+    from videogpa_b200.t5 import T5Config, T5EncoderModel
+    cfg = UMT5Config(vocab_size=100, d_model=256, d_kv=64, d_ff=512, num_layers=2, num_heads=4, feed_forward_proj="gated-gelu", dropout_rate=0.0)
+    torch.manual_seed(5)
+    m = UMT5EncoderModel(cfg).eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "layer_norm" in n:
+                p.copy_(1.0 + 0.1 * torch.randn_like(p))
+            elif "relative_attention_bias" in n:
+                p.copy_(0.5 * torch.randn_like(p))
+            elif "SelfAttention.q" in n:
+                p.copy_(torch.randn_like(p) * (256 * 64) ** -0.5 * 4)
+            elif "shared" in n or "embed_tokens" in n:
+                p.copy_(torch.randn_like(p))
+            else:
+                p.copy_(torch.randn_like(p) * p.shape[1] ** -0.5)
+            p.copy_(p.to(BF).float())
+    sd = m.state_dict()
+    tables = [sd[f"encoder.block.{i}.layer.0.SelfAttention.relative_attention_bias.weight"] for i in range(2)]
+    assert not torch.equal(tables[0], tables[1])                                      # the per-block tables really differ
+    c = T5Config(vocab_size=100, d_model=256, d_kv=64, d_ff=512, num_layers=2, num_heads=4, per_layer_relative_bias=True)
+    enc = T5EncoderModel(c, sd, device="cuda")
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(1, 100, (2, 40), generator=g)
+    with torch.no_grad():
+        ref = m(ids)[0]
+    got = enc(ids.cuda())[0].cpu().float()
+    err = (got - ref).abs().mean().item()
+    assert relmax(got, ref) < 3e-2 and err < 5e-3 * ref.abs().max().item(), (relmax(got, ref), err)
+    # a shared-table (plain T5) reading of the same weights must NOT match: the per-block tables matter
+    wrong = T5EncoderModel(T5Config(vocab_size=100, d_model=256, d_kv=64, d_ff=512, num_layers=2, num_heads=4), sd, device="cuda")
+    err_wrong = (wrong(ids.cuda())[0].cpu().float() - ref).abs().mean().item()
+    assert err_wrong > 5 * err, (err_wrong, err)
+    # Wan's call: padded to a fixed length with a mask; lengths 40 and 23
+    mask = torch.ones(2, 40, dtype=torch.long); mask[1, 23:] = 0
+    ids_p = ids.clone(); ids_p[1, 23:] = 0
+    with torch.no_grad():
+        ref_m = m(ids_p, attention_mask=mask)[0]
+    got_m = enc(ids_p.cuda(), attention_mask=mask.cuda())[0].cpu().float()
+    assert relmax(got_m[0], ref_m[0]) < 3e-2 and relmax(got_m[1, :23], ref_m[1, :23]) < 3e-2
+    assert float(got_m[1, 23:].abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        bad = mask.clone(); bad[0, 3] = 0                                              # a hole in the mask is not right padding
+        enc(ids_p.cuda(), attention_mask=bad.cuda())
+    assert T5Config.umt5_xxl().vocab_size == 256384 and T5Config.umt5_xxl().per_layer_relative_bias
+
+
 @pytest.mark.parametrize("B,H,S", [(2, 3, 75), (1, 2, 1), (1, 1, 512), (1, 4, 226), (3, 1, 33)])
 def test_t5_attention_op_vs_torch(lib, B, H, S):
     """vgpa_t5_attention_bf16 alone: no 1/sqrt(d) scaling, additive bias, bf16 roundings of scores and probabilities."""

@@ -196,3 +196,25 @@ def test_flow_unipc_scheduler_orders_and_schedule():
         FlowUniPCMultistepScheduler().step(torch.zeros(1), torch.zeros(1))
     with pytest.raises(RuntimeError):
         sch.set_timesteps(3, sigmas=[0.5, 0.6, 0.2, 0.1])
+
+
+def test_wan_umt5_checkpoint_name_mapping():
+    """t5.wan_umt5_to_transformers_names: Wan's own umT5 parameter names -> transformers' UMT5EncoderModel names (the mapping is
+    recalled, so the test pins its behaviour, not the Wan repository): every rule, and a loud failure on an unknown key."""
+    from videogpa_b200.t5 import wan_umt5_to_transformers_names as f
+    src = {"token_embedding.weight": 0, "norm.weight": 1, "blocks.0.norm1.weight": 2, "blocks.0.norm2.weight": 3, "blocks.23.attn.q.weight": 4,
+           "blocks.23.attn.k.weight": 5, "blocks.23.attn.v.weight": 6, "blocks.23.attn.o.weight": 7, "blocks.7.pos_embedding.embedding.weight": 8,
+           "blocks.7.ffn.gate.0.weight": 9, "blocks.7.ffn.fc1.weight": 10, "blocks.7.ffn.fc2.weight": 11}
+    out = f(src)
+    assert out == {"shared.weight": 0, "encoder.final_layer_norm.weight": 1, "encoder.block.0.layer.0.layer_norm.weight": 2,
+                   "encoder.block.0.layer.1.layer_norm.weight": 3, "encoder.block.23.layer.0.SelfAttention.q.weight": 4,
+                   "encoder.block.23.layer.0.SelfAttention.k.weight": 5, "encoder.block.23.layer.0.SelfAttention.v.weight": 6,
+                   "encoder.block.23.layer.0.SelfAttention.o.weight": 7,
+                   "encoder.block.7.layer.0.SelfAttention.relative_attention_bias.weight": 8,
+                   "encoder.block.7.layer.1.DenseReluDense.wi_0.weight": 9, "encoder.block.7.layer.1.DenseReluDense.wi_1.weight": 10,
+                   "encoder.block.7.layer.1.DenseReluDense.wo.weight": 11}
+    with pytest.raises(RuntimeError, match="unexpected parameter"):
+        f({"blocks.0.attn.q.bias": 0})
+    from pathlib import Path
+    from videogpa_b200.generate.wan2_2_ti2v_5b import WanPromptEncoder
+    assert WanPromptEncoder.available(Path("/nonexistent")) is False

@@ -10,7 +10,8 @@ What runs here: the guided denoise loop of `WanTI2V.generate` on videogpa_b200 k
 timesteps (first latent frame t = 0 and clamped to the encoded image), cond / uncond forwards, `uncond + g (cond - uncond)`,
 shifted flow-matching schedule (`--shift`) and the UniPC multistep sampler that `WanTI2V.generate` defaults to
 (schedulers.FlowUniPCMultistepScheduler; `sample_solver="euler"` selects the fused Euler step). The un-vendored Wan2.2
-repository's umT5 text encoder and Wan-VAE are outside this build, so the result of a prompt is the final latent
+repository's Wan-VAE is outside this build (and its umT5 text encoder runs here only when the checkpoint directory carries it:
+`WanPromptEncoder`), so the result of a prompt is the final latent
 `seed_<seed>.latents.pt` ([48, F, h, w], bf16) instead of an mp4, and inputs are either synthetic (`--synthetic N`: N-block
 random DiT, context / first-frame latent seeded from the prompt and image bytes) or precomputed next to the image:
 `<image>.context.pt` ([L <= 512, 4096]), `<image>.latent.pt` ([48, 1, h, w]) and the encoded negative prompt
@@ -100,6 +101,43 @@ class WanTI2VEngine:
         return lat
 
 
+class WanPromptEncoder:
+    """`self.text_encoder([prompt], device)` of `WanTI2V.generate`: umT5-XXL over the prompt padded to `text_len` = 512 with a mask,
+    output trimmed to the true length -> context [L, 4096]. Runs on videogpa_b200.t5 (umT5 = one relative-position table per block).
+    Loaded only when the checkpoint directory carries the encoder: `models_t5_umt5-xxl-enc-bf16.pth` (Wan's parameter names, mapped by
+    t5.wan_umt5_to_transformers_names) or `text_encoder/` in transformers' layout, plus the tokenizer under `google/umt5-xxl/`."""
+
+    TEXT_LEN = 512
+
+    def __init__(self, model_path: Path, device):
+        from transformers import AutoTokenizer
+        from ..t5 import T5Config, T5EncoderModel, wan_umt5_to_transformers_names
+        pth = model_path / "models_t5_umt5-xxl-enc-bf16.pth"
+        if pth.is_file():
+            sd = wan_umt5_to_transformers_names(torch.load(str(pth), map_location="cpu"))
+        elif (model_path / "text_encoder").is_dir():
+            from .cogvideox_5b import _load_safetensors_dir
+            sd = _load_safetensors_dir(model_path / "text_encoder")
+        else:
+            raise RuntimeError("no umT5 weights in the checkpoint directory")
+        self.tok = AutoTokenizer.from_pretrained(str(model_path / "google" / "umt5-xxl"))
+        self.enc = T5EncoderModel(T5Config.umt5_xxl(), sd, device=device)
+        self.device = device
+
+    @staticmethod
+    def available(model_path: Path) -> bool:
+        return ((model_path / "models_t5_umt5-xxl-enc-bf16.pth").is_file() or (model_path / "text_encoder").is_dir()) and \
+            (model_path / "google" / "umt5-xxl").is_dir()
+
+    @torch.no_grad()
+    def __call__(self, prompt: str) -> torch.Tensor:
+        text = " ".join(prompt.split())                              # whitespace clean-up of Wan's tokenizer wrapper
+        t = self.tok([text], padding="max_length", truncation=True, max_length=self.TEXT_LEN, add_special_tokens=True, return_tensors="pt")
+        ids, mask = t.input_ids.to(self.device), t.attention_mask.to(self.device)
+        L = int(mask.sum())
+        return self.enc(ids, attention_mask=mask)[0][0, :L].cpu()
+
+
 def _seeded(path_or_text, shape, salt: str):
     data = Path(path_or_text).read_bytes() if salt == "img" else path_or_text.encode()
     seed = int.from_bytes(hashlib.sha256(data).digest()[:4], "little")
@@ -153,6 +191,10 @@ def generate(args):
             merge_lora(model, args.lora_path, weight=args.lora_weight)
             print("LoRA merged.")
     engine = WanTI2VEngine(model, device)
+    prompt_encoder = None
+    if not args.synthetic and WanPromptEncoder.available(Path(args.model_path)):
+        print("Loading umT5 prompt encoder")
+        prompt_encoder = WanPromptEncoder(Path(args.model_path), device)
     tasks = load_tasks(args.prompt_json, args.num_prompts)
     if tasks is None:
         print("Unsupported JSON format")
@@ -185,17 +227,28 @@ def generate(args):
                 first = _seeded(image_path, (cfg.in_dim, 1, h, w), "img")
             else:
                 cpath, lpath = Path(str(image_path) + ".context.pt"), Path(str(image_path) + ".latent.pt")
-                if not cpath.exists() or not lpath.exists():
-                    raise RuntimeError(f"{cpath.name} / {lpath.name} not found: umT5 and the Wan-VAE are outside this build")
-                context, first = torch.load(str(cpath), map_location="cpu"), torch.load(str(lpath), map_location="cpu")
-                # the unconditional branch sees the encoded negative prompt: per image, else one shared file in the model directory
+                if not lpath.exists():
+                    raise RuntimeError(f"{lpath.name} not found: the Wan-VAE (first-frame latent) is outside this build")
+                first = torch.load(str(lpath), map_location="cpu")
+                if cpath.exists():
+                    context = torch.load(str(cpath), map_location="cpu")
+                elif prompt_encoder is not None:
+                    context = prompt_encoder(text_prompt)
+                else:
+                    raise RuntimeError(f"{cpath.name} not found and the checkpoint directory has no umT5 encoder")
+                # the unconditional branch sees the encoded negative prompt: per image, else one shared file in the model directory,
+                # else <model_path>/negative_prompt.txt (the configuration's sample_neg_prompt) through the umT5 encoder
                 npath = Path(str(image_path) + ".null_context.pt")
                 if not npath.exists():
                     npath = Path(args.model_path) / "null_context.pt"
-                if not npath.exists():
-                    raise RuntimeError(f"{Path(str(image_path)).name}.null_context.pt / {npath} not found: the umT5 encoding of the "
-                                       "negative prompt is needed for the unconditional branch")
-                null_context = torch.load(str(npath), map_location="cpu")
+                ntxt = Path(args.model_path) / "negative_prompt.txt"
+                if npath.exists():
+                    null_context = torch.load(str(npath), map_location="cpu")
+                elif prompt_encoder is not None and ntxt.is_file():
+                    null_context = prompt_encoder(ntxt.read_text(encoding="utf-8"))
+                else:
+                    raise RuntimeError(f"{Path(str(image_path)).name}.null_context.pt / {npath} / {ntxt.name} not found: the umT5 encoding of "
+                                       "the negative prompt is needed for the unconditional branch")
             if args.synthetic:
                 null_context = _seeded("negative prompt", (32, cfg.text_dim), "txt")
             lat = engine.generate(context, first, frame_num=args.frame_num, shift=args.shift, sampling_steps=args.sampling_steps,

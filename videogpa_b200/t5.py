@@ -36,6 +36,13 @@ class T5Config:
     relative_attention_num_buckets: int = 32
     relative_attention_max_distance: int = 128
     layer_norm_epsilon: float = 1e-6
+    per_layer_relative_bias: bool = False   # umT5 (transformers UMT5EncoderModel; Wan2.2's text encoder): every block has its own table
+
+    @classmethod
+    def umt5_xxl(cls) -> "T5Config":
+        """google/umt5-xxl, the text encoder of Wan2.2 (generate/Wan2.2-TI2V-5B.py via the Wan repository): T5 v1.1 geometry, 256 384-token
+        vocabulary, one relative-position table per block."""
+        return cls(vocab_size=256384, per_layer_relative_bias=True)
 
 
 def relative_position_bucket(relative_position: torch.Tensor, num_buckets: int = 32, max_distance: int = 128) -> torch.Tensor:
@@ -56,6 +63,37 @@ def position_buckets(S: int, num_buckets: int = 32, max_distance: int = 128) -> 
     ctx = torch.arange(S, dtype=torch.long)[:, None]
     mem = torch.arange(S, dtype=torch.long)[None, :]
     return relative_position_bucket(mem - ctx, num_buckets, max_distance)
+
+
+def wan_umt5_to_transformers_names(sd: dict) -> dict:
+    """Rename the parameters of Wan2.2's own umT5 encoder module (`models_t5_umt5-xxl-enc-bf16.pth`, wan/modules/t5.py of the
+    un-vendored Wan repository) to transformers' UMT5EncoderModel names, which this encoder loads. **[recalled]** — the Wan
+    repository is not in the reference tree, so the source names below could not be checked here; a checkpoint with other names
+    fails loudly (missing key) instead of loading wrongly.
+        token_embedding.weight                      -> shared.weight
+        blocks.{i}.norm1.weight / norm2.weight      -> encoder.block.{i}.layer.0 / layer.1 .layer_norm.weight
+        blocks.{i}.attn.{q,k,v,o}.weight            -> encoder.block.{i}.layer.0.SelfAttention.{q,k,v,o}.weight
+        blocks.{i}.pos_embedding.embedding.weight   -> encoder.block.{i}.layer.0.SelfAttention.relative_attention_bias.weight
+        blocks.{i}.ffn.gate.0.weight / fc1 / fc2    -> encoder.block.{i}.layer.1.DenseReluDense.wi_0 / wi_1 / wo .weight
+        norm.weight                                 -> encoder.final_layer_norm.weight"""
+    import re
+    out = {}
+    rules = [(r"^token_embedding\.weight$", "shared.weight"), (r"^norm\.weight$", "encoder.final_layer_norm.weight"),
+             (r"^blocks\.(\d+)\.norm1\.weight$", r"encoder.block.\1.layer.0.layer_norm.weight"),
+             (r"^blocks\.(\d+)\.norm2\.weight$", r"encoder.block.\1.layer.1.layer_norm.weight"),
+             (r"^blocks\.(\d+)\.attn\.([qkvo])\.weight$", r"encoder.block.\1.layer.0.SelfAttention.\2.weight"),
+             (r"^blocks\.(\d+)\.pos_embedding\.embedding\.weight$", r"encoder.block.\1.layer.0.SelfAttention.relative_attention_bias.weight"),
+             (r"^blocks\.(\d+)\.ffn\.gate\.0\.weight$", r"encoder.block.\1.layer.1.DenseReluDense.wi_0.weight"),
+             (r"^blocks\.(\d+)\.ffn\.fc1\.weight$", r"encoder.block.\1.layer.1.DenseReluDense.wi_1.weight"),
+             (r"^blocks\.(\d+)\.ffn\.fc2\.weight$", r"encoder.block.\1.layer.1.DenseReluDense.wo.weight")]
+    for k, v in sd.items():
+        for pat, rep in rules:
+            if re.match(pat, k):
+                out[re.sub(pat, rep, k)] = v
+                break
+        else:
+            raise RuntimeError(f"unexpected parameter {k!r} in a Wan umT5 checkpoint")
+    return out
 
 
 class T5EncoderOutput(tuple):
@@ -97,6 +135,7 @@ class T5EncoderModel:
             a = f"encoder.block.{i}.layer.0."
             f = f"encoder.block.{i}.layer.1."
             b = SimpleNamespace()
+            b.rel_bias = w16(a + "SelfAttention.relative_attention_bias.weight") if c.per_layer_relative_bias else None
             b.ln0 = w32(a + "layer_norm.weight")
             b.wqkv = torch.cat([w16(a + "SelfAttention.q.weight"), w16(a + "SelfAttention.k.weight"),
                                 w16(a + "SelfAttention.v.weight")], 0).contiguous()
@@ -127,6 +166,8 @@ class T5EncoderModel:
               "encoder.final_layer_norm.weight": (1.0 + 0.1 * torch.randn(c.d_model, generator=g, device=dev)).to(BF16)}
         for i in range(c.num_layers):
             a, f = f"encoder.block.{i}.layer.0.", f"encoder.block.{i}.layer.1."
+            if c.per_layer_relative_bias and i > 0:
+                sd[a + "SelfAttention.relative_attention_bias.weight"] = rnd(c.relative_attention_num_buckets, c.num_heads, std=0.5)
             sd[a + "layer_norm.weight"] = (1.0 + 0.1 * torch.randn(c.d_model, generator=g, device=dev)).to(BF16)
             sd[a + "SelfAttention.q.weight"] = rnd(inner, c.d_model, std=(c.d_model * c.d_kv) ** -0.5)
             sd[a + "SelfAttention.k.weight"] = rnd(inner, c.d_model, std=c.d_model ** -0.5)
@@ -145,13 +186,16 @@ class T5EncoderModel:
         return self
 
     # ------------------------------------------------------------------ pieces
-    def position_bias(self, S: int) -> torch.Tensor:
-        """[H, S, S] bf16: relative_attention_bias(bucket(j - i)) permuted like T5Attention.compute_bias."""
-        b = self._bias_cache.get(S)
+    def position_bias(self, S: int, layer: int = 0) -> torch.Tensor:
+        """[H, S, S] bf16: relative_attention_bias(bucket(j - i)) permuted like T5Attention.compute_bias. T5 shares block 0's table
+        over all blocks; umT5 (`per_layer_relative_bias`) gives every block its own (UMT5Attention.compute_bias per layer)."""
+        key = (S, layer if self.config.per_layer_relative_bias else 0)
+        b = self._bias_cache.get(key)
         if b is None:
             c = self.config
+            table = self.blocks[layer].rel_bias if c.per_layer_relative_bias else self.rel_bias
             bk = position_buckets(S, c.relative_attention_num_buckets, c.relative_attention_max_distance).to(self.device)
-            b = self._bias_cache[S] = self.rel_bias[bk].permute(2, 0, 1).contiguous()
+            b = self._bias_cache[key] = table[bk].permute(2, 0, 1).contiguous()
         return b
 
     def _rmsnorm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
@@ -171,7 +215,9 @@ class T5EncoderModel:
         if input_ids.dim() != 2:
             raise RuntimeError("input_ids must be [B, S]")
         if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
-            raise RuntimeError("attention masks with padding are not supported (the reference passes none)")
+            if not self.config.per_layer_relative_bias:
+                raise RuntimeError("attention masks with padding are not supported (the reference passes none)")
+            return self._masked(input_ids, attention_mask)
         B, S = input_ids.shape
         if S > 512:
             raise RuntimeError("sequence length above 512 is not supported")
@@ -196,15 +242,31 @@ class T5EncoderModel:
         g.replay()
         return T5EncoderOutput((static_out.clone(),))
 
+    def _masked(self, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> T5EncoderOutput:
+        """umT5 as Wan2.2 calls it: prompts padded to text_len with a mask, the output trimmed to the true lengths. Masked keys do
+        not take part in attention and the position bias is relative, so the rows of the real tokens equal an unmasked run over
+        the unpadded prefix: every sample is encoded at its own length; rows at padded positions are returned as zeros (transformers
+        computes values there that every caller discards)."""
+        m = attention_mask.to(torch.bool)
+        lens = m.sum(dim=1)
+        if not bool((m == (torch.arange(m.shape[1], device=m.device)[None] < lens[:, None])).all()) or int(lens.min()) == 0:
+            raise RuntimeError("only right-padded attention masks with at least one token per sample are supported")
+        B, S = input_ids.shape
+        out = torch.zeros((B, S, self.config.d_model), dtype=BF16, device=self.device)
+        for b in range(B):
+            L = int(lens[b])
+            out[b, :L] = self(input_ids[b:b + 1, :L])[0][0]
+        return T5EncoderOutput((out,))
+
     def _forward(self, ids: torch.Tensor) -> torch.Tensor:
         lib = _lib.load()
         B, S = ids.shape
         c = self.config
         x = self.embed.index_select(0, ids.reshape(-1)).contiguous()                               # [B*S, d_model]
-        bias = self.position_bias(S)
         M, inner = B * S, self.inner
         stream = _lib.current_stream
-        for b in self.blocks:
+        for li, b in enumerate(self.blocks):
+            bias = self.position_bias(S, li)
             n = self._rmsnorm(x, b.ln0)
             qkv = dense.linear(n, b.wqkv)
             ctx = torch.empty((M, inner), dtype=BF16, device=self.device)
