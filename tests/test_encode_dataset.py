@@ -76,3 +76,15 @@ def test_encode_groups_and_chain_to_dataset(tmp_path):
     assert len(pairs) == 1 and pairs[0]["winner"]["latent_path"].endswith("latent_G1_a.pt") and pairs[0]["loser"]["latent_path"].endswith("latent_G1_b.pt")
     assert E.process_t2v_encoding(str(base / "none.json"), str(out), str(base), FakeVAE(), FakeT5(), tok) is None
     assert E.extract_groups({"groups": [1]}) == [1] and E.extract_groups(5) == []
+    # the I2V variant: image_embeds in the condition file, files under <latent_root>/processed, whole group kept, groups without image skipped
+    from PIL import Image
+    Image.fromarray(np.full((40, 60, 3), 128, dtype=np.uint8)).save(base / "first.png")
+    gi = [dict(groups[0], image_path="first.png"), groups[0]]
+    inp.write_text(json.dumps({"groups": gi}))
+    ri = E.process_t2v_encoding(str(inp), str(base / "meta_i2v.json"), str(base), FakeVAE(), FakeT5(), tok, latent_root=str(base / "i2v_latent"),
+                                image_condition=True, sub_folder="processed")
+    assert len(ri["groups"]) == 1 and ri["groups"][0]["extra"] == 1 and ri["groups"][0]["image_path"] == "first.png"
+    vi = ri["groups"][0]["videos"][0]
+    assert vi["condition_path"] == "i2v_latent/processed/cond_G1.pt"
+    ci = torch.load(str(base / vi["condition_path"]))
+    assert tuple(ci["image_embeds"].shape) == (3, 40, 60) and abs(float(ci["image_embeds"].mean()) - 128 / 255) < 1e-6

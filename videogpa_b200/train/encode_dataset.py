@@ -44,20 +44,38 @@ def encode_video_file(vae_encoder, video_full_path, num_frames: int = 49, scale_
     return latent.squeeze(0).cpu()
 
 
+def load_input_image_tensor(image_path) -> torch.Tensor | None:
+    """train/CogVideoX-I2V-5B/02_encode.py:65-69: RGB image -> float [3, H, W] in [0, 1] (None when the file is missing)."""
+    import numpy as np
+    from PIL import Image
+    p = Path(image_path)
+    if not p.exists():
+        return None
+    arr = np.array(Image.open(p).convert("RGB")).astype(np.float32) / 255.0
+    return torch.from_numpy(arr).permute(2, 0, 1)
+
+
 def encode_groups(groups_chunk: list, base_path, latent_root, vae_encoder, text_encoder, tokenize_fn, num_frames: int = 49,
-                  scale_latents: bool = False, generator=None, tag: str = "Worker-0") -> list:
-    """The loop of `gpu_worker` (02_encode.py:161-214)."""
-    base_path, out = Path(base_path), Path(latent_root)
+                  scale_latents: bool = False, generator=None, tag: str = "Worker-0", image_condition: bool = False, sub_folder: str = "") -> list:
+    """The loop of `gpu_worker` (02_encode.py:161-214). image_condition: the I2V variant (train/CogVideoX-I2V-5B/02_encode.py:72-99,
+    :144-176) — groups need an `image_path`, the conditioning image is stored as `image_embeds` in the condition file, files go under
+    `<latent_root>/<sub_folder>` ("processed" there) and the whole input group is kept, not only {group_id, text_prompt, videos}."""
+    base_path, out = Path(base_path), Path(latent_root) / sub_folder
     out.mkdir(parents=True, exist_ok=True)
     processed = []
     for group in groups_chunk:
         prompt, group_id, entries = group.get("text_prompt"), group.get("group_id"), group.get("videos", [])
-        if not prompt or not entries:
-            logging.warning(f"Group {group_id} missing prompt or videos, skipped.")
+        if not prompt or not entries or (image_condition and not group.get("image_path")):
+            logging.warning(f"Group {group_id} missing prompt, videos or image, skipped.")
             continue
         try:
             cond_path = out / f"cond_{group_id}.pt"
-            torch.save(encode_text_condition(text_encoder, tokenize_fn(prompt)), cond_path)
+            cond = encode_text_condition(text_encoder, tokenize_fn(prompt))
+            if image_condition:
+                img = load_input_image_tensor(base_path / group["image_path"])
+                if img is not None:
+                    cond["image_embeds"] = img
+            torch.save(cond, cond_path)
             videos = []
             for entry in entries:
                 rel = entry.get("video_path")
@@ -78,7 +96,12 @@ def encode_groups(groups_chunk: list, base_path, latent_root, vae_encoder, text_
                     logging.error(f"Video {rel} Encoding Error: {ex}")
                     continue
             if videos:
-                processed.append({"group_id": group_id, "text_prompt": prompt, "videos": videos})
+                if image_condition:
+                    kept = dict(group)
+                    kept["videos"] = videos
+                    processed.append(kept)
+                else:
+                    processed.append({"group_id": group_id, "text_prompt": prompt, "videos": videos})
         except Exception as ex:                                    # noqa: BLE001
             logging.error(f"Group {group_id} Encoding Error: {ex}")
             continue
@@ -86,7 +109,8 @@ def encode_groups(groups_chunk: list, base_path, latent_root, vae_encoder, text_
 
 
 def process_t2v_encoding(input_json: str, output_json: str, base_path: str, vae_encoder, text_encoder, tokenize_fn,
-                         latent_root: str | None = None, num_frames: int = 49, scale_latents: bool = False, generator=None):
+                         latent_root: str | None = None, num_frames: int = 49, scale_latents: bool = False, generator=None,
+                         image_condition: bool = False, sub_folder: str = ""):
     """02_encode.py:219-262. -> {"groups": [...]} as written to `output_json` (rank 0), None otherwise."""
     data = safe_load_json(input_json)
     if not data:
@@ -103,7 +127,7 @@ def process_t2v_encoding(input_json: str, output_json: str, base_path: str, vae_
         from ..parallel import init_from_env
         rank, world, _ = init_from_env()
     mine = encode_groups(all_groups[rank::world], base_path, latent_root, vae_encoder, text_encoder, tokenize_fn, num_frames, scale_latents,
-                         generator, tag=f"Worker-{rank}")
+                         generator, tag=f"Worker-{rank}", image_condition=image_condition, sub_folder=sub_folder)
     if world > 1:
         import torch.distributed as dist
         gathered = [None] * world
