@@ -73,6 +73,26 @@ def test_scheduler_from_checkpoint_config(tmp_path):
         CogVideoXDPMScheduler.from_pretrained(str(tmp_path / "missing"))
 
 
+def test_i2v_checkpoint_scheduler_selection(tmp_path):
+    """generate/CogVideoX-5B-I2V.py:16-19 and replicate.py:158-162 keep the scheduler the checkpoint ships (no swap to DPM): the class
+    comes from scheduler_config.json's `_class_name`."""
+    from videogpa_b200.generate.cogvideox_5b_i2v import checkpoint_scheduler
+    from videogpa_b200.schedulers import CogVideoXDDIMScheduler, CogVideoXDPMScheduler
+    (tmp_path / "scheduler").mkdir()
+    cfg = {"_class_name": "CogVideoXDDIMScheduler", "beta_start": 0.00085, "beta_end": 0.012, "beta_schedule": "scaled_linear",
+           "num_train_timesteps": 1000, "prediction_type": "v_prediction", "rescale_betas_zero_snr": True, "snr_shift_scale": 1.0,
+           "timestep_spacing": "trailing"}
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(cfg))
+    assert type(checkpoint_scheduler(str(tmp_path))) is CogVideoXDDIMScheduler
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(dict(cfg, _class_name="CogVideoXDPMScheduler")))
+    assert type(checkpoint_scheduler(str(tmp_path))) is CogVideoXDPMScheduler
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(dict(cfg, _class_name="EulerDiscreteScheduler")))
+    with pytest.raises(RuntimeError, match="not implemented"):
+        checkpoint_scheduler(str(tmp_path))
+    with pytest.raises(RuntimeError):
+        checkpoint_scheduler(str(tmp_path / "missing"))
+
+
 def test_rope_table_matches_oracle():
     from videogpa_b200.rope import get_3d_rotary_pos_embed
     cfg = O.DiTConfig()

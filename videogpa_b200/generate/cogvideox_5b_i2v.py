@@ -65,6 +65,22 @@ def first_frame_latent(image_path, shape, device, encoder, scaling_factor: float
     return lat
 
 
+def checkpoint_scheduler(base_model):
+    """The scheduler `CogVideoXImageToVideoPipeline.from_pretrained` builds: class and settings from `<base_model>/scheduler/
+    scheduler_config.json` (CogVideoX-5B-I2V ships CogVideoXDDIMScheduler)."""
+    import json
+    from ..schedulers import CogVideoXDDIMScheduler, CogVideoXDPMScheduler
+    sc_file = Path(base_model) / "scheduler" / "scheduler_config.json"
+    if not sc_file.is_file():
+        raise RuntimeError(f"{sc_file} not found")
+    sc = json.loads(sc_file.read_text())
+    known = {"CogVideoXDDIMScheduler": CogVideoXDDIMScheduler, "CogVideoXDPMScheduler": CogVideoXDPMScheduler}
+    name = sc.get("_class_name", "CogVideoXDDIMScheduler")
+    if name not in known:
+        raise RuntimeError(f"scheduler class {name!r} is not implemented")
+    return known[name].from_config(sc)
+
+
 def build_parser():
     p = base.build_parser()
     p.description = "CogVideoX-5B I2V generation"
@@ -95,17 +111,7 @@ def generate(args):
         prompts = base._SyntheticPrompts(cfg.text_embed_dim, device)
     else:
         pipe, prompts = base.build_pipeline(args, device, with_encoder=True)
-        # the I2V script keeps the checkpoint's own scheduler (:16-19, no swap): class and settings from scheduler_config.json
-        import json
-        from ..schedulers import CogVideoXDPMScheduler
-        sc_file = Path(args.base_model) / "scheduler" / "scheduler_config.json"
-        if not sc_file.is_file():
-            raise RuntimeError(f"{sc_file} not found")
-        sc = json.loads(sc_file.read_text())
-        known = {"CogVideoXDDIMScheduler": CogVideoXDDIMScheduler, "CogVideoXDPMScheduler": CogVideoXDPMScheduler}
-        if sc.get("_class_name", "CogVideoXDDIMScheduler") not in known:
-            raise RuntimeError(f"scheduler class {sc.get('_class_name')!r} is not implemented")
-        pipe.scheduler = known[sc.get("_class_name", "CogVideoXDDIMScheduler")].from_config(sc)
+        pipe.scheduler = checkpoint_scheduler(args.base_model)      # the I2V script keeps the checkpoint's own scheduler (:16-19, no swap)
     if args.lora_path:
         if not os.path.exists(args.lora_path):
             print(f"LoRA path not found: {args.lora_path}, using base model")

@@ -145,6 +145,7 @@ def worker(rank: int, gpu_id: int, json_items: list, config: dict, synthetic: in
         prompts = base._SyntheticPrompts(cfg.text_embed_dim, device)
     else:
         pipe, prompts = base.build_pipeline(args, device, with_encoder=True)
+        pipe.scheduler = i2v.checkpoint_scheduler(args.base_model)    # CogVideoXImageToVideoPipeline keeps the checkpoint's scheduler
     pipe.vae.enable_tiling(); pipe.vae.enable_slicing()
     handle = None
     if mode in LORA_MODES and config["lora_path"]:
